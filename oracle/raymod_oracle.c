@@ -1,0 +1,448 @@
+/*
+ * raymod_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).  See raymod_oracle.h.
+ *
+ * Every function cites the reference lines it restates; paths are relative to
+ * /root/reference/.  "sq" = subroutineR-quiet.f90, "ll" = ray_tracing_sampling/loglhood.f90.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math -fopenmp (see oracle/Makefile).
+ * No FMA, no reassociation: the bits must equal gfortran -O2 on baseline x86-64.
+ */
+#include "raymod_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_TOL            1.0e-1   /* sq:234, sq:351   tol = 1.d-1                     */
+#define ORC_NEWTON_MAXIT   15       /* sq:233                                            */
+#define ORC_BISECT_MAXIT   20       /* sq:346                                            */
+#define ORC_CLAMP_RR       1.0e-9   /* sq:250  rr = 1d-9                                 */
+#define ORC_SAFE_EPS       1.0e-10  /* sq:142, sq:388                                    */
+#define ORC_BISECT_LO      1.0e-10  /* sq:148  first bracket end                         */
+#define ORC_BISECT_HI_EPS  1.0e-12  /* sq:148  1/maxval(vp) - 1d-12                      */
+#define ORC_HALVE_CAP      2200     /* the reference loops forever on NaN p0 (sq:125-133);
+                                       2200 halvings take any finite double to 0          */
+#define ORC_PI             3.141592653589793238462643383279502884197 /* data_type.f90:5 */
+
+
+/* gfortran list-directed output of a REAL(8) (the format of rays.dat, sq:101-102,160-161):
+   17 significant digits, fixed notation for 0.1 <= |x| < 1e17 (right-justified in 21 columns
+   followed by 5 blanks), exponent form otherwise. */
+static void fprint_ld(FILE *fh, double x)
+{
+    char buf[64];
+    double ax = fabs(x);
+    if (x == 0.0) {
+        snprintf(buf, sizeof buf, "0.0000000000000000");
+    } else if (ax >= 0.1 && ax < 1e17) {
+        int e10 = (int)floor(log10(ax));
+        int dec = 16 - e10;
+        if (e10 < 0) dec = 17;
+        if (dec < 0) dec = 0;
+        snprintf(buf, sizeof buf, "%.*f", dec, x);
+    } else {
+        int e10 = (int)floor(log10(ax));
+        double m = x / pow(10.0, e10);
+        snprintf(buf, sizeof buf, "%.16fE%+04d", m, e10);
+        fprintf(fh, "%26s", buf);
+        return;
+    }
+    fprintf(fh, "%21s     ", buf);
+}
+
+/* ---- sq:9-32 whichLayer ------------------------------------------------------------ */
+int orc_which_layer(const double *depths, int nlayers, double dph)
+{
+    int    inN  = 0;
+    double diff = 0.0;  /* uninitialised in the reference when nlayers == 0 (never called so) */
+    for (int i = 1; i <= nlayers; ++i) {
+        inN  = i;
+        diff = depths[i - 1] - dph;
+        if (diff > 0.0) break;
+    }
+    if (nlayers <= 0) return 1;          /* defined extension: a bare half-space */
+    return (diff < 0.0) ? nlayers + 1 : inN;
+}
+
+/* ---- sq:184-202 costFunc ----------------------------------------------------------- */
+static double cost_f(double x, const double *H, const double *V, int n, double R)
+{
+    double sum_all = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double num = (H[i] * V[i]) * x;                       /* H*V*x, left to right */
+        double den = sqrt(1.0 - (x * x) * (V[i] * V[i]));     /* sqrt(1-(x**2)*V**2)  */
+        sum_all = sum_all + num / den;
+    }
+    return R - sum_all;
+}
+
+/* ---- sq:206-221 costFunc_Prime ----------------------------------------------------- */
+static double cost_fp(double x, const double *H, const double *V, int n)
+{
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double s     = sqrt(1.0 - (x * x) * (V[i] * V[i]));
+        double denom = s * (s * s);                           /* s**3 */
+        acc = acc + (H[i] * V[i]) / denom;
+    }
+    return -acc;
+}
+
+static double max_of(const double *V, int n)
+{
+    double m = V[0];
+    for (int i = 1; i < n; ++i) if (V[i] > m) m = V[i];
+    return m;
+}
+
+/* ---- sq:226-332 solve (Newton) ----------------------------------------------------- */
+static double newton_solve(double x0, const double *H, const double *V, int n, double R,
+                           int *conv_out, orc_trace *tr, int x0_cached)
+{
+    int    conv = 0;
+    double x = x0, fx = 0.0, fxp = 0.0;
+    int    k;
+    for (k = 1; k <= ORC_NEWTON_MAXIT; ++k) {
+        fx  = cost_f(x, H, V, n, R);                           /* sq:275 */
+        fxp = cost_fp(x, H, V, n);                             /* sq:284 */
+        if (tr) {
+            tr->n_f_ref++; tr->n_fp_ref++;
+            int cached = (k == 1) && x0_cached;                /* caller already holds f,f' at x0 */
+            if (fabs(fx) < ORC_TOL) { if (!cached) tr->n_f_min++; }
+            else if (!cached) tr->n_ffp_min++;
+        }
+        if (fabs(fx) < ORC_TOL) { conv = 1; break; }           /* sq:287-291 */
+        x = x - fx / fxp;                                      /* sq:294-298 */
+        if (tr) tr->n_newton++;
+        if (x > 1.0 / max_of(V, n)) {                          /* sq:299-304 */
+            x = 1.0 / max_of(V, n) - ORC_CLAMP_RR;
+            if (tr) tr->n_clamp++;
+        }
+    }
+    if (k > ORC_NEWTON_MAXIT) {                                /* sq:314-317 */
+        fx = cost_f(x, H, V, n, R);
+        if (tr) { tr->n_f_ref++; tr->n_f_min++; }
+    }
+    if (fabs(fx) > ORC_TOL) conv = 1;                          /* sq:327-330 (sic) */
+    if (tr) tr->f_final = fx;
+    *conv_out = conv;
+    return x;
+}
+
+/* ---- sq:339-405 solvebst (bisection until a Newton jump is safe) ------------------- */
+static double bisect_solve(double x1, double x2, const double *H, const double *V, int n,
+                           double R, orc_trace *tr, int *x_cached)
+{
+    double fmid = cost_f(x2, H, V, n, R);                      /* sq:353 */
+    double f    = cost_f(x1, H, V, n, R);                      /* sq:354 */
+    double x, dx, xmid, fx, fxp, check_x;
+    (void)fmid;
+    if (tr) { tr->n_f_ref += 2; tr->n_f_min += 2; }
+    if (f < 0.0) { x = x1; dx = x2 - x1; }                     /* sq:359-365 */
+    else         { x = x2; dx = x1 - x2; }
+    *x_cached = 0;
+    for (int k = 1; k <= ORC_BISECT_MAXIT; ++k) {
+        dx   = dx * 0.5;                                       /* sq:368 */
+        xmid = x + dx;                                         /* sq:369 */
+        fmid = cost_f(xmid, H, V, n, R);                       /* sq:370 */
+        if (tr) { tr->n_bisect++; tr->n_f_ref++; }
+        *x_cached = 0;
+        if (fmid < 0.0) { x = xmid; *x_cached = 1; }           /* sq:371-373 */
+        if (fmid == 0.0) { if (tr) tr->n_f_min++; break; }     /* sq:375-377 */
+        fx  = cost_f(xmid, H, V, n, R);                        /* sq:378 */
+        fxp = cost_fp(xmid, H, V, n);                          /* sq:380 */
+        if (tr) { tr->n_f_ref++; tr->n_fp_ref++; tr->n_ffp_min++; }
+        check_x = x - fx / fxp;                                /* sq:384-386: x, not xmid */
+        if (check_x < 1.0 / max_of(V, n) - ORC_SAFE_EPS) {     /* sq:388-392 */
+            x = xmid; *x_cached = 1;
+            break;
+        }
+        if (fabs(fmid) < ORC_TOL) break;                       /* sq:394-396 */
+    }
+    return x;
+}
+
+/* ---- sq:77-178 GetPTime on the truncated column H[0..n-1], V[0..n-1] --------------- */
+static double get_ptime(double src_depth, double src_offset, int n,
+                        const double *V, const double *H, orc_trace *tr,
+                        int keep_delta, const char *rays_path)
+{
+    double timeP;
+    if (n == 1) {                                              /* sq:94-97 */
+        timeP = sqrt(src_depth * src_depth + src_offset * src_offset) / V[0];
+        if (tr) {
+            tr->branch = ORC_BRANCH_TOP; tr->conv = 1;
+            /* the reference has no p on this path; report the straight ray's sin(theta)/v */
+            tr->p = (src_offset / sqrt(src_depth * src_depth + src_offset * src_offset)) / V[0];
+        }
+        if (keep_delta > 0 && rays_path) {                     /* sq:98-105 (root copy only) */
+            FILE *fh = fopen(rays_path, "a");
+            if (fh) {
+                fprint_ld(fh, src_offset); fprintf(fh, "\n");
+                fprint_ld(fh, src_depth);  fprintf(fh, "\n");
+                fclose(fh);
+            }
+        }
+        return timeP;
+    }
+
+    int    conv = 0;
+    double hv_sum = 0.0;
+    for (int i = 0; i < n; ++i) hv_sum = hv_sum + H[i] / V[i];
+    double c_harmonic = src_depth / hv_sum;                                            /* sq:112 */
+    double cos_t = src_depth / sqrt(src_offset * src_offset + src_depth * src_depth);  /* sq:113 */
+    double p0 = cos_t / c_harmonic * 1.0;                                              /* sq:116 */
+
+    for (int guard = 0; guard < ORC_HALVE_CAP; ++guard) {                              /* sq:125-133 */
+        double s = 0.0;
+        for (int i = 0; i < n; ++i)
+            s = s + sqrt(1.0 - (p0 * p0) * ((V[i] + 1.0) * (V[i] + 1.0)));
+        if (!isnan(s)) break;
+        p0 = p0 / 2.0;
+        if (tr) tr->n_halve++;
+    }
+
+    double cf  = cost_f(p0, H, V, n, src_offset);                                      /* sq:136 */
+    double cfp = cost_fp(p0, H, V, n);                                                 /* sq:137 */
+    double check_x = p0 - cf / cfp;                                                    /* sq:138 */
+    if (tr) { tr->n_f_ref++; tr->n_fp_ref++; tr->n_ffp_min++; }
+
+    double p_final;
+    if (cf < 0.0) {                                                                    /* sq:139-141 */
+        if (tr) tr->branch = ORC_BRANCH_NEG;
+        p_final = newton_solve(p0, H, V, n, src_offset, &conv, tr, 1);
+    } else if (check_x < 1.0 / max_of(V, n) - ORC_SAFE_EPS) {                          /* sq:142-144 */
+        if (tr) tr->branch = ORC_BRANCH_SAFE;
+        p_final = newton_solve(p0, H, V, n, src_offset, &conv, tr, 1);
+    } else {                                                                           /* sq:145-153 */
+        int cached = 0;
+        if (tr) tr->branch = ORC_BRANCH_BISECT;
+        double pb = bisect_solve(ORC_BISECT_LO, 1.0 / max_of(V, n) - ORC_BISECT_HI_EPS,
+                                 H, V, n, src_offset, tr, &cached);
+        p_final = newton_solve(pb, H, V, n, src_offset, &conv, tr, cached);
+    }
+
+    /* sq:156,165-166  cosV = sqrt(1-(p**2)*vp**2); t_int = depths/(vp*cosV); sum */
+    timeP = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double cosV = sqrt(1.0 - (p_final * p_final) * (V[i] * V[i]));
+        timeP = timeP + H[i] / (V[i] * cosV);
+    }
+    if (keep_delta > 0 && rays_path) {                                                 /* sq:157-164 */
+        FILE *fh = fopen(rays_path, "a");
+        if (fh) {
+            for (int i = 0; i < n; ++i) {
+                double cosV = sqrt(1.0 - (p_final * p_final) * (V[i] * V[i]));
+                double q = H[i] / cosV;
+                fprint_ld(fh, sqrt(q * q - H[i] * H[i]));
+            }
+            fprintf(fh, "\n");
+            for (int i = 0; i < n; ++i) fprint_ld(fh, H[i]);
+            fprintf(fh, "\n");
+            fclose(fh);
+        }
+    }
+    if (!conv) timeP = -999.0;                                                         /* sq:167-169 */
+    if (tr) { tr->p = p_final; tr->conv = conv; }
+    return timeP;
+}
+
+/* ---- sq:436-455 one trip of the source loop: whichLayer, InsertLayer, GetPTime ------ */
+static double ray_time_impl(const double *vels, const double *depths, int nlayers,
+                            double src_offset, double src_depth, orc_trace *tr,
+                            int keep_delta, const char *rays_path)
+{
+    if (tr) memset(tr, 0, sizeof *tr);
+    int nl = orc_which_layer(depths, nlayers, src_depth);
+    if (tr) tr->nl = nl;
+    if (nl == 1)                                               /* sq:438-441 */
+        return get_ptime(src_depth, src_offset, 1, vels, depths, tr, keep_delta, rays_path);
+
+    /* sq:38-69 InsertLayer: the column above the source, interfaces turned into thicknesses.
+       Both branches (:51-56 and :57-63) give V(1:nl) = vels(1:nl) and depths_new(1:nl) =
+       (z(1:nl-1), dph); :67 differences it in place. */
+    double Hs[64], Vs[64];
+    double *H = Hs, *V = Vs;
+    if (nl > 64) {
+        H = (double *)malloc(sizeof(double) * (size_t)nl * 2);
+        V = H + nl;
+    }
+    for (int i = 0; i < nl; ++i) V[i] = vels[i];
+    H[0] = depths[0];
+    for (int i = 1; i < nl - 1; ++i) H[i] = depths[i] - depths[i - 1];
+    H[nl - 1] = src_depth - depths[nl - 2];
+    double t = get_ptime(src_depth, src_offset, nl, V, H, tr, keep_delta, rays_path);
+    if (H != Hs) free(H);
+    return t;
+}
+
+double orc_ray_time(const double *vels, const double *depths, int nlayers,
+                    double src_offset, double src_depth, orc_trace *tr)
+{
+    return ray_time_impl(vels, depths, nlayers, src_offset, src_depth, tr, -1, NULL);
+}
+
+/* ---- sq:408-463 dofullforwardproblem == sq:467-520 TraceRays ------------------------ */
+void orc_trace_rays(const double *vels, const double *depths, int nlayers,
+                    const double *src_offset, const double *src_depth, int nsrc,
+                    double *timeP, double *p_out, orc_trace *traces,
+                    int keep_delta, const char *rays_path)
+{
+    for (int k = 0; k < nsrc; ++k) timeP[k] = -1.0;            /* sq:430 */
+    if (rays_path) {                                           /* sq:432-433: REPLACE, every call */
+        FILE *fh = fopen(rays_path, "w");
+        if (fh) fclose(fh);
+    }
+    for (int k = 0; k < nsrc; ++k) {                           /* sq:434-462 */
+        orc_trace local;
+        orc_trace *tr = traces ? &traces[k] : (p_out ? &local : NULL);
+        timeP[k] = ray_time_impl(vels, depths, nlayers, src_offset[k], src_depth[k], tr,
+                                 keep_delta, rays_path);
+        if (p_out) p_out[k] = tr->p;
+    }
+}
+
+/* ---- ll:165-166,193-203 ------------------------------------------------------------ */
+double orc_loglhood_from_times(const double *tpred, const double *tobs, int ndat, double sigma)
+{
+    double ss = 0.0;
+    for (int k = 0; k < ndat; ++k) {
+        double res = tobs[k] - tpred[k];                       /* ll:166 */
+        ss = ss + res * res;                                   /* SUM(DresRT**2) */
+    }
+    double n = (double)ndat;
+    double logL = log(1.0 / pow(2.0 * ORC_PI, n / 2.0))        /* ll:194 */
+                - (ss / (2.0 * (sigma * sigma)) + n * log(sigma));   /* ll:195-196 */
+    if (isnan(logL)) logL = -DBL_MAX;                          /* ll:200-203 */
+    return logL;
+}
+
+/* ---- ll:127-146 model mapping + ll:165-203 ------------------------------------------ */
+double orc_loglhood_rt(int k, const double *vp, const double *ziface,
+                       const double *src_offset, const double *src_depth, int nsrc,
+                       const double *tobs, double sigma, double *tpred)
+{
+    double *pred = tpred ? tpred : (double *)malloc(sizeof(double) * (size_t)(nsrc > 0 ? nsrc : 1));
+    if (k > 1) {
+        orc_trace_rays(vp, ziface, k - 1, src_offset, src_depth, nsrc, pred, NULL, NULL, -1, NULL);
+    } else {
+        double v2[2] = { vp[0], vp[0] };
+        double z1[1] = { 9999.9 };
+        orc_trace_rays(v2, z1, 1, src_offset, src_depth, nsrc, pred, NULL, NULL, -1, NULL);
+    }
+    double logL = orc_loglhood_from_times(pred, tobs, nsrc, sigma);
+    if (!tpred) free(pred);
+    return logL;
+}
+
+/* ---- batched sweeps (workload shape of replica.f90:173-232; new, not in the reference) */
+int orc_dff_batch(const double *vels, const double *depths, const int *nlayers,
+                  int B, int ldv, int ldz,
+                  const double *src_offset, const double *src_depth, int nsrc,
+                  double *timeP, const double *tobs, const double *sigma,
+                  double *logL, double *p_out, int nthreads)
+{
+    int used = 1;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+    used = nthreads;
+#else
+    (void)nthreads;
+#endif
+#pragma omp parallel num_threads(used)
+    {
+        double *tloc = (double *)malloc(sizeof(double) * (size_t)(nsrc > 0 ? nsrc : 1));
+        double *ploc = (double *)malloc(sizeof(double) * (size_t)(nsrc > 0 ? nsrc : 1));
+#pragma omp for schedule(dynamic, 64)
+        for (int b = 0; b < B; ++b) {
+            const double *v = vels + (size_t)b * ldv;
+            const double *z = depths + (size_t)b * ldz;
+            double *t = timeP ? timeP + (size_t)b * nsrc : tloc;
+            double *p = p_out ? p_out + (size_t)b * nsrc : NULL;
+            orc_trace_rays(v, z, nlayers[b], src_offset, src_depth, nsrc, t, p, NULL, -1, NULL);
+            if (logL) logL[b] = orc_loglhood_from_times(t, tobs, nsrc, sigma[b]);
+        }
+        free(tloc); free(ploc);
+    }
+    return used;
+}
+
+int orc_dff_batch_faithful(const double *vels, const double *depths, const int *nlayers,
+                           int B, int ldv, int ldz,
+                           const double *src_offset, const double *src_depth, int nsrc,
+                           double *timeP, const char *rays_path)
+{
+    double *tloc = (double *)malloc(sizeof(double) * (size_t)(nsrc > 0 ? nsrc : 1));
+    for (int b = 0; b < B; ++b) {
+        double *t = timeP ? timeP + (size_t)b * nsrc : tloc;
+        orc_trace_rays(vels + (size_t)b * ldv, depths + (size_t)b * ldz, nlayers[b],
+                       src_offset, src_depth, nsrc, t, NULL, NULL, -1, rays_path);
+    }
+    free(tloc);
+    return 1;
+}
+
+/* ---- work accounting (DESIGN.md "work per evaluation"; sqrt = div = 1 flop) --------- */
+void orc_batch_stats(const double *vels, const double *depths, const int *nlayers,
+                     int B, int ldv, int ldz,
+                     const double *src_offset, const double *src_depth, int nsrc,
+                     orc_stats *out)
+{
+    orc_stats s;
+    memset(&s, 0, sizeof s);
+    for (int b = 0; b < B; ++b) {
+        for (int k = 0; k < nsrc; ++k) {
+            orc_trace tr;
+            (void)orc_ray_time(vels + (size_t)b * ldv, depths + (size_t)b * ldz, nlayers[b],
+                               src_offset[k], src_depth[k], &tr);
+            double L = (double)tr.nl;
+            s.rays++;
+            s.sum_nl += tr.nl;
+            if (tr.branch == ORC_BRANCH_TOP) {
+                s.top++;
+                s.flops_ref += 5.0; s.flops_min += 5.0;
+                s.sqrt_ref += 1; s.div_ref += 1; s.sqrt_min += 1; s.div_min += 1;
+                continue;
+            }
+            if (tr.branch == ORC_BRANCH_NEG)    s.neg++;
+            if (tr.branch == ORC_BRANCH_SAFE)   s.safe++;
+            if (tr.branch == ORC_BRANCH_BISECT) s.bisect++;
+            s.n_halve += tr.n_halve; s.n_bisect += tr.n_bisect; s.n_newton += tr.n_newton;
+            s.n_clamp += tr.n_clamp; s.not_conv += !tr.conv;
+            s.n_f_ref += tr.n_f_ref; s.n_fp_ref += tr.n_fp_ref;
+            s.n_ffp_min += tr.n_ffp_min; s.n_f_min += tr.n_f_min;
+            int isb = tr.branch == ORC_BRANCH_BISECT;
+            /* what the reference executes */
+            s.flops_ref += (L - 1.0)                       /* InsertLayer differencing            */
+                         + (2.0 * L + 1.0) + 5.0 + 2.0      /* c_harmonic, cos_t, p0               */
+                         + (6.0 * L + 1.0) * (1 + tr.n_halve) + tr.n_halve
+                         + (8.0 * L + 2.0) * tr.n_f_ref + (9.0 * L + 2.0) * tr.n_fp_ref
+                         + 2.0 + 2.0                        /* check_x, 1/vmax - 1e-10             */
+                         + (isb ? 2.0 + 6.0 * tr.n_bisect : 0.0)
+                         + 3.0 * tr.n_newton + 2.0 * tr.n_clamp
+                         + (7.0 * L + 1.0);                 /* travel-time sum                      */
+            s.sqrt_ref += (long long)(L * (1 + tr.n_halve) + L * tr.n_f_ref + L * tr.n_fp_ref + L) + 1;
+            s.div_ref  += (long long)((L + 1) + 2 + tr.n_halve + L * tr.n_f_ref + L * tr.n_fp_ref
+                                      + 2 + (isb ? 1 + 2 * tr.n_bisect : 0) + 2 * tr.n_newton
+                                      + tr.n_clamp + L);
+            /* de-duplicated count that still yields identical bits */
+            s.flops_min += 5.0 + 5.0 + 1.0                  /* last-layer H, hv, c_h; cos_t; p0    */
+                         + 5.0 * (1 + tr.n_halve) + tr.n_halve
+                         + 1.0 + 1.0                        /* 1/vmax, - 1e-10                      */
+                         + (10.0 * L + 3.0) * tr.n_ffp_min + (6.0 * L + 2.0) * tr.n_f_min
+                         + 2.0                              /* check_x                              */
+                         + (isb ? 1.0 + 4.0 * tr.n_bisect : 0.0)
+                         + 2.0 * tr.n_newton + 1.0 * tr.n_clamp
+                         + (6.0 * L + 1.0);
+            s.sqrt_min += (long long)(1 + L * tr.n_ffp_min + L * tr.n_f_min + L);
+            s.div_min  += (long long)(2 + 1 + 1 + tr.n_halve + 1 + 2 * L * tr.n_ffp_min + L * tr.n_f_min
+                                      + 1 + (isb ? tr.n_bisect : 0) + tr.n_newton + L);
+        }
+    }
+    *out = s;
+}

@@ -1,0 +1,113 @@
+/*
+ * raymod_oracle.h -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ *
+ * A plain-C restatement of the reference's 1-D layered-cake forward ray tracer
+ * (module raymod, /root/reference/subroutineR-quiet.f90) and of the Gaussian
+ * travel-time likelihood (LOGLHOOD_RT, /root/reference/ray_tracing_sampling/loglhood.f90).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library.  The product (raytracerfortran_b200/) never does.
+ *
+ * Parity status: PINNED.  The restatement is checked against the reference's own
+ * full-precision ray dump (rays.dat, 20 rays) and the rendered notebook's 5 printed
+ * travel times (tests/test_oracle_golden.py).  The reference Fortran itself cannot be
+ * compiled in this image (no Fortran compiler of any kind), so oracle/_ref/ is empty.
+ *
+ * Numerics contract: IEEE-754 binary64, round-to-nearest, NO fused multiply-add,
+ * sums accumulated left to right from 0 -- what gfortran -O2 emits on baseline x86-64
+ * for the array expressions of the reference.  Compile with -O2 -ffp-contract=off.
+ */
+#ifndef RAYMOD_ORACLE_H
+#define RAYMOD_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Which path GetPTime took for one ray (subroutineR-quiet.f90:94,139,142,145). */
+enum {
+    ORC_BRANCH_TOP    = 0,  /* source in the top layer: straight ray          */
+    ORC_BRANCH_NEG    = 1,  /* f(p0) < 0           -> Newton from p0          */
+    ORC_BRANCH_SAFE   = 2,  /* first Newton jump is safe -> Newton from p0    */
+    ORC_BRANCH_BISECT = 3   /* bisection first, then Newton                   */
+};
+
+/* Per-ray trace of the solver trajectory.  Filled when a non-NULL pointer is given. */
+typedef struct {
+    double p;          /* ray parameter the travel time was summed at (p_final)          */
+    double f_final;    /* last value of the offset misfit f seen by solve()              */
+    int    nl;         /* 1-based index of the layer holding the source (whichLayer)     */
+    int    branch;     /* ORC_BRANCH_*                                                   */
+    int    n_halve;    /* p0 halvings in the NaN guard (:125-133)                        */
+    int    n_bisect;   /* bisection iterations executed (loop trips of solvebst)         */
+    int    n_newton;   /* Newton updates x <- x - f/f' applied in solve()                */
+    int    n_clamp;    /* times solve() clamped x to 1/vmax - 1e-9 (:299-304)            */
+    int    conv;       /* the reference's `conv` flag at exit (quirk at :327-330)        */
+    int    n_f_ref;    /* costFunc calls the reference executes                          */
+    int    n_fp_ref;   /* costFunc_Prime calls the reference executes                    */
+    int    n_ffp_min;  /* distinct points where BOTH f and f' are consumed               */
+    int    n_f_min;    /* distinct points where only f is consumed                       */
+} orc_trace;
+
+/* whichLayer, subroutineR-quiet.f90:9-32.  Returns the 1-based layer index. */
+int orc_which_layer(const double *depths, int nlayers, double dph);
+
+/* One ray: whichLayer + InsertLayer + GetPTime (subroutineR-quiet.f90:436-455).
+ * vels[nlayers+1], depths[nlayers] (interface depths from the surface). */
+double orc_ray_time(const double *vels, const double *depths, int nlayers,
+                    double src_offset, double src_depth, orc_trace *tr);
+
+/* dofullforwardproblem / TraceRays, subroutineR-quiet.f90:408-463 / :467-520.
+ * p_out and traces may be NULL.  keep_delta > 0 rewrites ./rays_path like the
+ * reference rewrites ./rays.dat (pass NULL for rays_path to skip the file). */
+void orc_trace_rays(const double *vels, const double *depths, int nlayers,
+                    const double *src_offset, const double *src_depth, int nsrc,
+                    double *timeP, double *p_out, orc_trace *traces,
+                    int keep_delta, const char *rays_path);
+
+/* The Gaussian log-likelihood of LOGLHOOD_RT (loglhood.f90:165-166,193-203),
+ * NMODE = 1, ICOV = 1, IAR = 0. */
+double orc_loglhood_from_times(const double *tpred, const double *tobs, int ndat, double sigma);
+
+/* Batched sweep over models (the workload shape of replica.f90 / configs 2-5).
+ * vels[B][ldv], depths[B][ldz], nlayers[B]; sources shared by every model.
+ * timeP[B][nsrc], p_out[B][nsrc], logL[B] may each be NULL; logL needs tobs, sigma[B].
+ * nthreads <= 0 -> all OpenMP threads.  Returns the thread count used. */
+int orc_dff_batch(const double *vels, const double *depths, const int *nlayers,
+                  int B, int ldv, int ldz,
+                  const double *src_offset, const double *src_depth, int nsrc,
+                  double *timeP, const double *tobs, const double *sigma,
+                  double *logL, double *p_out, int nthreads);
+
+/* "Faithful" variant of the batched sweep: one model per call AND the per-call
+ * open/truncate/close of rays.dat the reference performs (:432-433). */
+int orc_dff_batch_faithful(const double *vels, const double *depths, const int *nlayers,
+                           int B, int ldv, int ldz,
+                           const double *src_offset, const double *src_depth, int nsrc,
+                           double *timeP, const char *rays_path);
+
+/* LOGLHOOD_RT's model mapping (loglhood.f90:127-146): k Voronoi nodes with P velocities
+ * vp[0..k-1] and interface depths ziface[0..k-2]; k == 1 -> two equal velocities over one
+ * fake interface at 9999.9.  Returns logL; tpred[ndat] (may be NULL) gets DpredRT. */
+double orc_loglhood_rt(int k, const double *vp, const double *ziface,
+                       const double *src_offset, const double *src_depth, int nsrc,
+                       const double *tobs, double sigma, double *tpred);
+
+/* Aggregate trace counters over a batch (for W_ref / W_min flop accounting). */
+typedef struct {
+    long long rays, top, neg, safe, bisect;
+    long long sum_nl, n_halve, n_bisect, n_newton, n_clamp, not_conv;
+    long long n_f_ref, n_fp_ref, n_ffp_min, n_f_min;
+    double    flops_ref, flops_min;   /* see DESIGN.md "work per evaluation" */
+    long long sqrt_ref, div_ref, sqrt_min, div_min;
+} orc_stats;
+
+void orc_batch_stats(const double *vels, const double *depths, const int *nlayers,
+                     int B, int ldv, int ldz,
+                     const double *src_offset, const double *src_depth, int nsrc,
+                     orc_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
