@@ -1,0 +1,124 @@
+/*
+ * raytrace_b200.h -- C ABI of libraytrace_b200.so: the B200 (sm_100a) drop-in for the
+ * reference's one data-parallel hot path, the 1-D layered-cake forward ray tracer `dff`
+ * fused with the Gaussian travel-time likelihood.
+ *
+ * Reference = AntonBiryukovUofC/RayTracerFortran; citations are file:line in that tree.
+ *
+ * Conventions shared by every entry point
+ *   - plain pointers and sizes only; every scalar of the Fortran-facing entries is passed
+ *     BY REFERENCE (what R's .Fortran / .C and Fortran bind(C) callers without VALUE do);
+ *   - all reals are IEEE binary64 (c_double), all counts are 32-bit (c_int);
+ *   - vels[NLayers+1]  layer P velocities, surface to half-space;
+ *     depths[NLayers]  depths of the interfaces below the surface (NOT thicknesses,
+ *                      raytracerR-export-data-to-MCMC.Rmd:61);
+ *   - the caller owns every buffer; the library keeps no result state between calls
+ *     (device buffers and streams are cached internally and reused);
+ *   - one calling thread per process; one process per GPU (device = RTB200_DEVICE, else
+ *     LOCAL_RANK, else 0, unless rtb200_init() chose one);
+ *   - there is NO CPU fallback: without a usable CUDA device the Fortran-style entries fill
+ *     their outputs with NaN, print one line to stderr and record rtb200_last_error();
+ *     the int-returning entries return a non-zero status.
+ *   - results are bit-identical to the reference algorithm evaluated in IEEE binary64
+ *     without FMA contraction ("parity").
+ */
+#ifndef RAYTRACE_B200_H
+#define RAYTRACE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Drop-in symbols of the reference
+ * ---------------------------------------------------------------------------------------- */
+
+/* Replaces  subroutine dofullforwardproblem(...) bind(C, name="dff_")
+ *           subroutineR-quiet.f90:408-463   (the symbol R's .Fortran("dff", ...) resolves,
+ *           rayTracerR.R:31-33, raytracerR-export-data-to-MCMC.Rmd:81-83).
+ * timeP[k] = direct-ray travel time from source k to the surface receiver; -999 when the
+ * reference's `conv` flag stays false (:167-169).  keep_delta > 0 (re)writes ./rays.dat
+ * with the per-layer horizontal advances and thicknesses of every ray (:157-164). */
+void dff_(const double *vels, const double *depths, const int *NLayers,
+          const double *src_offset, const double *src_depth, const int *NSrc,
+          double *timeP, const int *keep_delta);
+
+/* The older 7-argument form: subroutineR.f90:405, README.md:16-21, adaptMCMC.Rmd:74-78.
+ * A C callee cannot see a missing 8th argument, so the two arities are two symbols; build
+ * with -DRTB200_DFF_IS_7ARG to export this one under the name dff_ instead. */
+void dff7_(const double *vels, const double *depths, const int *NLayers,
+           const double *src_offset, const double *src_depth, const int *NSrc,
+           double *timeP);
+
+/* Replaces  subroutine TraceRays(...)  subroutineR-quiet.f90:467-520, the entry the sampler's
+ * likelihood calls (ray_tracing_sampling/loglhood.f90:135,144).  Same body as dff_.  The
+ * Fortran shim shim/raymod_b200.f90 forwards module raymod's TraceRays to this symbol. */
+void tracerays_(const double *vels, const double *depths, const int *NLayers,
+                const double *src_offset, const double *src_depth, const int *NSrc,
+                double *timeP, const int *keep_delta);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched entries (new; the reference evaluates one model per call)
+ * ---------------------------------------------------------------------------------------- */
+
+/* B models x NSrc sources in one call; the sources are shared by every model, as in the
+ * reference (rjmcmc_com.f90:44-45).  Host pointers.
+ *   vels   [B][ldv]  row b holds nlayers[b]+1 velocities   (Fortran: vels(ldv,B))
+ *   depths [B][ldz]  row b holds nlayers[b]   interfaces   (Fortran: depths(ldz,B))
+ *   timeP  [B][NSrc] or NULL      travel times
+ *   p_out  [B][NSrc] or NULL      ray parameter the travel time was summed at
+ *   logL   [B]       or NULL      fused LOGLHOOD_RT value (needs tobs[NSrc], sigma[B]):
+ *                                 log(1/(2 pi)^(N/2)) - (sum(res^2)/(2 sigma^2) + N log sigma),
+ *                                 NaN -> -HUGE            (loglhood.f90:165-166,193-203)
+ * Returns 0, or a non-zero status (see rtb200_last_error()). */
+int dff_batch(const double *vels, const double *depths, const int *nlayers,
+              const int *B, const int *ldv, const int *ldz,
+              const double *src_offset, const double *src_depth, const int *NSrc,
+              double *timeP, const double *tobs, const double *sigma,
+              double *logL, double *p_out);
+
+/* LOGLHOOD / LOGLHOOD_RT (loglhood.f90:3-32,35-211) over B chain states, with the model
+ * mapping of :127-146: state b has k[b] Voronoi nodes, vp[b][0..k-1] = voro(1:k,2),
+ * ziface[b][0..k-2] = ziface(1:k-1); k == 1 becomes two equal velocities over one fake
+ * interface at 9999.9.  NMODE = 1, ICOV = 1, IAR = 0 (every shipped configuration).
+ *   logL [B]; tpred [B][NSrc] or NULL receives DpredRT. */
+int loglhood_batch(const int *k, const double *vp, const double *ziface,
+                   const int *B, const int *ldv, const int *ldz,
+                   const double *src_offset, const double *src_depth, const int *NSrc,
+                   const double *tobs, const double *sigma,
+                   double *logL, double *tpred);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-resident entry: every pointer is a CUDA device pointer on the current device and
+ * nothing is copied.  Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ * library's own stream, in which case the call synchronises before returning).
+ * kmode != 0 : nlayers[] holds node counts k and the LOGLHOOD_RT mapping above is applied.
+ * ---------------------------------------------------------------------------------------- */
+int rtb200_dff_batch_device(const double *d_vels, const double *d_depths, const int *d_nlayers,
+                            int B, int ldv, int ldz,
+                            const double *d_src_offset, const double *d_src_depth, int NSrc,
+                            double *d_timeP, const double *d_tobs, const double *d_sigma,
+                            double *d_logL, double *d_p_out, int kmode, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Runtime control and introspection
+ * ---------------------------------------------------------------------------------------- */
+int         rtb200_init(int device);          /* optional; lazy init picks the device itself   */
+void        rtb200_shutdown(void);
+const char *rtb200_last_error(void);          /* "" when the last call succeeded               */
+int         rtb200_device_count(void);        /* 0 without a driver / device                   */
+/* options: "variant" (0 lock-step loops, 1 lane state machine), "threads", "tile_models",
+ *          "tile_sources", "chunk_models", "ctas_per_sm"; <= 0 restores the default */
+int         rtb200_set_option(const char *name, double value);
+/* stats of the last batched call: "kernel_ms", "total_ms", "launches" (cumulative),
+ *          "tile_models", "tile_sources", "smem_bytes", "grid", "threads", "ctas_per_sm" */
+double      rtb200_get_stat(const char *name);
+/* sustained FP64 FMA throughput of the current device in TFLOP/s (roofline denominator) */
+double      rtb200_fp64_peak_tflops(int repeats);
+/* contiguous slice [*lo, *hi) of B models owned by `rank` of `world` (model-axis sharding) */
+void        rtb200_shard_range(long long B, int rank, int world, long long *lo, long long *hi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

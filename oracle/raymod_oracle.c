@@ -142,7 +142,8 @@ static double bisect_solve(double x1, double x2, const double *H, const double *
     double f    = cost_f(x1, H, V, n, R);                      /* sq:354 */
     double x, dx, xmid, fx, fxp, check_x;
     (void)fmid;
-    if (tr) { tr->n_f_ref += 2; tr->n_f_min += 2; }
+    /* f(x2) is dead in the reference: fmid is overwritten at sq:370 before any use */
+    if (tr) { tr->n_f_ref += 2; tr->n_f_min += 1; }
     if (f < 0.0) { x = x1; dx = x2 - x1; }                     /* sq:359-365 */
     else         { x = x2; dx = x1 - x2; }
     *x_cached = 0;

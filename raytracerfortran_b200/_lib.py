@@ -1,0 +1,75 @@
+"""ctypes binding of libraytrace_b200.so -- the C ABI declared in include/raytrace_b200.h.
+
+Loading never falls back to anything: a missing library is an ImportError-like RuntimeError,
+a missing GPU makes every compute call raise.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libraytrace_b200.so")
+
+# every symbol include/raytrace_b200.h declares
+EXPORTS = (
+    "dff_", "dff7_", "tracerays_", "dff_batch", "loglhood_batch", "rtb200_dff_batch_device",
+    "rtb200_init", "rtb200_shutdown", "rtb200_last_error", "rtb200_device_count",
+    "rtb200_set_option", "rtb200_get_stat", "rtb200_fp64_peak_tflops", "rtb200_shard_range",
+)
+
+_lib = None
+
+
+class RayTraceError(RuntimeError):
+    """A call into libraytrace_b200 failed (no GPU, CUDA error, bad geometry)."""
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RayTraceError(
+            f"{LIB_PATH} is missing: build it with `python -m raytracerfortran_b200.build` "
+            "(there is no CPU fallback for this path)")
+    lib = C.CDLL(LIB_PATH)
+    dp, ip, i, d = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int, C.c_double
+    vp = C.c_void_p
+    lib.dff_.restype = None
+    lib.dff_.argtypes = [dp, dp, ip, dp, dp, ip, dp, ip]
+    lib.tracerays_.restype = None
+    lib.tracerays_.argtypes = [dp, dp, ip, dp, dp, ip, dp, ip]
+    lib.dff7_.restype = None
+    lib.dff7_.argtypes = [dp, dp, ip, dp, dp, ip, dp]
+    lib.dff_batch.restype = i
+    lib.dff_batch.argtypes = [dp, dp, ip, ip, ip, ip, dp, dp, ip, dp, dp, dp, dp, dp]
+    lib.loglhood_batch.restype = i
+    lib.loglhood_batch.argtypes = [ip, dp, dp, ip, ip, ip, dp, dp, ip, dp, dp, dp, dp]
+    lib.rtb200_dff_batch_device.restype = i
+    lib.rtb200_dff_batch_device.argtypes = [vp, vp, vp, i, i, i, vp, vp, i, vp, vp, vp, vp, vp, i, vp]
+    lib.rtb200_init.restype = i
+    lib.rtb200_init.argtypes = [i]
+    lib.rtb200_shutdown.restype = None
+    lib.rtb200_last_error.restype = C.c_char_p
+    lib.rtb200_device_count.restype = i
+    lib.rtb200_set_option.restype = i
+    lib.rtb200_set_option.argtypes = [C.c_char_p, d]
+    lib.rtb200_get_stat.restype = d
+    lib.rtb200_get_stat.argtypes = [C.c_char_p]
+    lib.rtb200_fp64_peak_tflops.restype = d
+    lib.rtb200_fp64_peak_tflops.argtypes = [i]
+    lib.rtb200_shard_range.restype = None
+    lib.rtb200_shard_range.argtypes = [C.c_longlong, i, i, C.POINTER(C.c_longlong),
+                                       C.POINTER(C.c_longlong)]
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().rtb200_last_error().decode()
+
+
+def check(rc=0):
+    """Raise if the last call reported a failure (status code or recorded error string)."""
+    err = last_error()
+    if rc != 0 or err:
+        raise RayTraceError(err or f"libraytrace_b200 status {rc}")

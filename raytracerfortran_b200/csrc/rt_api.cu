@@ -1,0 +1,552 @@
+// rt_api.cu -- the C ABI of libraytrace_b200.so (include/raytrace_b200.h) and the host-side
+// runtime around the kernels: device selection, cached device buffers, the chunked
+// H2D -> kernel -> D2H pipeline for host callers, tile geometry, rays.dat output.
+//
+// There is deliberately no CPU implementation of the path in this file: if CUDA is not
+// usable the entries report the failure (NaN outputs + stderr for the Fortran-style ones,
+// non-zero status for the others).
+#include "../../include/raytrace_b200.h"
+#include "rt_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+namespace {
+
+using rtb::BatchArgs;
+using rtb::TileCfg;
+
+constexpr double kPi = 3.141592653589793238462643383279502884197;  // data_type.f90:5 (PI2)
+constexpr int    kMaxChunks = 64;
+
+struct DevBuf {
+    void  *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct Ctx {
+    bool inited = false, ok = false;
+    int  device = 0, sms = 0, smem_optin = 0;
+    cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t  ev_h2d[kMaxChunks], ev_k0[kMaxChunks], ev_k1[kMaxChunks];
+    cudaEvent_t  ev_t0 = nullptr, ev_t1 = nullptr;
+    DevBuf vels, depths, nl, off, dep, cosv, tobs, sigma, timeP, pout, logL;
+    // options (<= 0: automatic)
+    int opt_variant = 1, opt_threads = 0, opt_tile_models = 0, opt_tile_sources = 0,
+        opt_chunk_models = 0, opt_ctas = 0;
+    // stats
+    double    kernel_ms = 0.0, total_ms = 0.0;
+    long long launches = 0;
+    TileCfg   last{};
+    int       last_ctas = 0;
+    std::string err;
+    bool warned = false;
+};
+
+Ctx g;
+
+int fail(const std::string &what, cudaError_t e = cudaSuccess) {
+    g.err = what;
+    if (e != cudaSuccess) {
+        g.err += ": ";
+        g.err += cudaGetErrorString(e);
+    }
+    return e != cudaSuccess ? (int)e : -1;
+}
+
+#define CK(call)                                                    \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return fail(#call, e__);            \
+    } while (0)
+
+int pick_device() {
+    const char *names[] = {"RTB200_DEVICE", "LOCAL_RANK"};
+    for (const char *n : names) {
+        const char *v = getenv(n);
+        if (v && *v) return atoi(v);
+    }
+    return 0;
+}
+
+int ensure_init(int device = -1) {
+    if (g.inited && (device < 0 || device == g.device)) {
+        if (!g.ok) return -1;
+        cudaSetDevice(g.device);
+        return 0;
+    }
+    if (g.inited && g.ok) rtb200_shutdown();
+    g.inited = true;
+    g.ok = false;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail("no usable CUDA device (libraytrace_b200 has no CPU fallback)", e);
+    g.device = device >= 0 ? device : pick_device();
+    if (g.device >= n) g.device = g.device % n;
+    CK(cudaSetDevice(g.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, g.device));
+    if (prop.major < 10)
+        return fail(std::string("device '") + prop.name +
+                    "' is not sm_100a; this library carries sm_100a code only");
+    g.sms = prop.multiProcessorCount;
+    CK(cudaDeviceGetAttribute(&g.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, g.device));
+    CK(cudaStreamCreateWithFlags(&g.s_comp, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxChunks; ++i) {
+        CK(cudaEventCreateWithFlags(&g.ev_h2d[i], cudaEventDisableTiming));
+        CK(cudaEventCreate(&g.ev_k0[i]));
+        CK(cudaEventCreate(&g.ev_k1[i]));
+    }
+    CK(cudaEventCreate(&g.ev_t0));
+    CK(cudaEventCreate(&g.ev_t1));
+    g.ok = true;
+    g.err.clear();
+    return 0;
+}
+
+int even_up(int x) { return (x + 1) & ~1; }
+
+// Tile geometry for one launch (DESIGN.md "tiling").
+int choose_cfg(int B, int ldv, int ldz, int nsrc, bool aligned, TileCfg &c) {
+    if (ldv > 255) return fail("more than 254 interfaces per model are not supported");
+    c.variant = g.opt_variant ? 1 : 0;
+    c.threads = g.opt_threads > 0 ? std::min(256, (g.opt_threads + 31) / 32 * 32) : 256;
+    c.LP = std::max(ldv, 2) | 1;
+    c.SC = std::min(nsrc, g.opt_tile_sources > 0 ? g.opt_tile_sources : 256);
+    c.TS = c.SC | 1;
+    c.use_tma = aligned ? 1 : 0;
+    const int rays_target = c.threads * 8;
+    int M = g.opt_tile_models > 0 ? g.opt_tile_models : std::max(2, rays_target / c.SC);
+    M = even_up(std::min(M, even_up(B)));
+    const int want_ctas = g.opt_ctas > 0 ? g.opt_ctas : 3;
+    const size_t budget  = (size_t)g.smem_optin;
+    const size_t per_cta = std::min<size_t>(budget, (size_t)(227 * 1024) / want_ctas - 1024);
+    for (;;) {
+        c.M = M;
+        c.smem = rtb::tile_smem_bytes(c, ldv, ldz);
+        const bool fits = c.smem <= per_cta && (size_t)M * c.SC <= 65536 &&
+                          (size_t)M * (ldv + ldz) * 8 < (1u << 20);
+        if (fits) break;
+        if (M > 2) { M = std::max(2, even_up(M / 2)); continue; }
+        if (c.SC > 32) { c.SC = std::max(32, c.SC / 2); c.TS = c.SC | 1; continue; }
+        if (c.smem <= budget) break;
+        return fail("model rows too large for shared memory");
+    }
+    int occ = rtb::max_ctas_per_sm(c);
+    if (occ < 1) return fail("batch kernel cannot be resident with this tile geometry");
+    // few models: shrink the tile so one wave of CTAs covers the batch
+    if (g.opt_tile_models <= 0 && (B + c.M - 1) / c.M < g.sms * occ) {
+        const int slots = g.sms * occ;
+        const int m2 = std::max(2, even_up((B + slots - 1) / slots));
+        if (m2 < c.M) {
+            c.M = m2;
+            c.smem = rtb::tile_smem_bytes(c, ldv, ldz);
+            occ = std::max(occ, rtb::max_ctas_per_sm(c));
+        }
+    }
+    const int ntiles = (B + c.M - 1) / c.M;
+    c.grid = std::max(1, std::min(ntiles, g.sms * occ));
+    g.last_ctas = occ;
+    return 0;
+}
+
+double log_norm_const(int nsrc) {
+    // LOG(1._RP/(2._RP*PI2)**(REAL(NDAT_RT,RP)/2._RP))     loglhood.f90:194
+    const double n = (double)nsrc;
+    return std::log(1.0 / std::pow(2.0 * kPi, n / 2.0));
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct HostCall {
+    const double *vels, *depths;
+    const int    *nlayers;
+    int B, ldv, ldz, kmode;
+    const double *off, *dep;
+    int nsrc;
+    double *timeP;
+    const double *tobs, *sigma;
+    double *logL, *p_out;
+};
+
+// Host buffers in, host buffers out: chunked over the model axis so the copy of chunk j+1
+// and the read-back of chunk j-1 overlap the kernel of chunk j.
+int run_host(const HostCall &h) {
+    if (int rc = ensure_init()) return rc;
+    g.err.clear();
+    g.kernel_ms = g.total_ms = 0.0;
+    if (h.B <= 0 || h.nsrc <= 0) return 0;
+    if (h.ldv < 1) return fail("ldv must be >= 1");
+    if (h.logL && (!h.tobs || !h.sigma)) return fail("logL needs tobs and sigma");
+    const size_t B = (size_t)h.B, S = (size_t)h.nsrc;
+    const int ldz = std::max(h.ldz, 0);
+
+    TileCfg cfg;
+    if (int rc = choose_cfg(h.B, h.ldv, ldz, h.nsrc, true, cfg)) return rc;
+    // our own buffers are padded to whole tiles, so TMA is always legal on them
+    const size_t Bpad = (B + cfg.M - 1) / cfg.M * cfg.M + cfg.M;
+    CK(g.vels.reserve(Bpad * h.ldv * 8));
+    CK(g.depths.reserve(Bpad * std::max(ldz, 1) * 8));
+    CK(g.nl.reserve(Bpad * 4));
+    CK(g.off.reserve(S * 8));
+    CK(g.dep.reserve(S * 8));
+    CK(g.cosv.reserve(S * 8));
+    if (h.tobs) CK(g.tobs.reserve(S * 8));
+    if (h.sigma) CK(g.sigma.reserve(B * 8));
+    if (h.timeP) CK(g.timeP.reserve(B * S * 8));
+    if (h.p_out) CK(g.pout.reserve(B * S * 8));
+    if (h.logL) CK(g.logL.reserve(B * 8));
+
+    CK(cudaEventRecord(g.ev_t0, g.s_h2d));
+    CK(cudaMemcpyAsync(g.off.p, h.off, S * 8, cudaMemcpyHostToDevice, g.s_h2d));
+    CK(cudaMemcpyAsync(g.dep.p, h.dep, S * 8, cudaMemcpyHostToDevice, g.s_h2d));
+    if (h.tobs) CK(cudaMemcpyAsync(g.tobs.p, h.tobs, S * 8, cudaMemcpyHostToDevice, g.s_h2d));
+    CK(rtb::launch_prep_sources(g.off.as<double>(), g.dep.as<double>(), g.cosv.as<double>(),
+                                h.nsrc, g.s_h2d));
+    g.launches++;
+
+    // chunk boundaries are multiples of the tile size
+    size_t chunk = g.opt_chunk_models > 0 ? (size_t)g.opt_chunk_models : (size_t)65536;
+    chunk = std::max(chunk, (B + kMaxChunks - 1) / kMaxChunks);
+    chunk = (chunk + cfg.M - 1) / cfg.M * cfg.M;
+    const int nchunks = (int)((B + chunk - 1) / chunk);
+
+    const double logc = h.logL ? log_norm_const(h.nsrc) : 0.0;
+    for (int j = 0; j < nchunks; ++j) {
+        const size_t j0 = (size_t)j * chunk, j1 = std::min(B, j0 + chunk), nb = j1 - j0;
+        CK(cudaMemcpyAsync(g.vels.as<double>() + j0 * h.ldv, h.vels + j0 * h.ldv, nb * h.ldv * 8,
+                           cudaMemcpyHostToDevice, g.s_h2d));
+        if (ldz > 0)
+            CK(cudaMemcpyAsync(g.depths.as<double>() + j0 * ldz, h.depths + j0 * ldz,
+                               nb * ldz * 8, cudaMemcpyHostToDevice, g.s_h2d));
+        CK(cudaMemcpyAsync(g.nl.as<int>() + j0, h.nlayers + j0, nb * 4, cudaMemcpyHostToDevice,
+                           g.s_h2d));
+        if (h.sigma)
+            CK(cudaMemcpyAsync(g.sigma.as<double>() + j0, h.sigma + j0, nb * 8,
+                               cudaMemcpyHostToDevice, g.s_h2d));
+        CK(cudaEventRecord(g.ev_h2d[j], g.s_h2d));
+
+        BatchArgs a{};
+        a.vels = g.vels.as<double>() + j0 * h.ldv;
+        a.depths = g.depths.as<double>() + j0 * ldz;
+        a.nlayers = g.nl.as<int>() + j0;
+        a.B = (int)nb; a.ldv = h.ldv; a.ldz = ldz; a.kmode = h.kmode;
+        a.src_offset = g.off.as<double>(); a.src_depth = g.dep.as<double>();
+        a.src_cos = g.cosv.as<double>(); a.tobs = h.tobs ? g.tobs.as<double>() : nullptr;
+        a.nsrc = h.nsrc;
+        a.sigma = h.sigma ? g.sigma.as<double>() + j0 : nullptr;
+        a.timeP = h.timeP ? g.timeP.as<double>() + j0 * S : nullptr;
+        a.p_out = h.p_out ? g.pout.as<double>() + j0 * S : nullptr;
+        a.logL = h.logL ? g.logL.as<double>() + j0 : nullptr;
+        a.logc = logc;
+        a.padded = 1;
+        TileCfg cj = cfg;
+        const int ntiles = (int)((nb + cfg.M - 1) / cfg.M);
+        cj.grid = std::max(1, std::min(ntiles, g.sms * g.last_ctas));
+        CK(cudaStreamWaitEvent(g.s_comp, g.ev_h2d[j], 0));
+        CK(cudaEventRecord(g.ev_k0[j], g.s_comp));
+        CK(rtb::launch_batch(a, cj, g.s_comp));
+        CK(cudaEventRecord(g.ev_k1[j], g.s_comp));
+        g.launches++;
+        g.last = cj;
+
+        CK(cudaStreamWaitEvent(g.s_d2h, g.ev_k1[j], 0));
+        if (h.timeP)
+            CK(cudaMemcpyAsync(h.timeP + j0 * S, a.timeP, nb * S * 8, cudaMemcpyDeviceToHost,
+                               g.s_d2h));
+        if (h.p_out)
+            CK(cudaMemcpyAsync(h.p_out + j0 * S, a.p_out, nb * S * 8, cudaMemcpyDeviceToHost,
+                               g.s_d2h));
+        if (h.logL)
+            CK(cudaMemcpyAsync(h.logL + j0, a.logL, nb * 8, cudaMemcpyDeviceToHost, g.s_d2h));
+    }
+    CK(cudaEventRecord(g.ev_t1, g.s_d2h));
+    CK(cudaStreamSynchronize(g.s_d2h));
+    CK(cudaStreamSynchronize(g.s_comp));
+    for (int j = 0; j < nchunks; ++j) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, g.ev_k0[j], g.ev_k1[j]));
+        g.kernel_ms += ms;
+    }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g.ev_t0, g.ev_t1) == cudaSuccess) g.total_ms = ms;
+    return 0;
+}
+
+void nan_fill(double *p, size_t n) {
+    if (!p) return;
+    for (size_t i = 0; i < n; ++i) p[i] = std::numeric_limits<double>::quiet_NaN();
+}
+
+void complain() {
+    if (!g.warned) {
+        fprintf(stderr, "libraytrace_b200: %s\n", g.err.c_str());
+        g.warned = true;
+    }
+}
+
+// gfortran list-directed REAL(8): 17 significant digits (the look of the reference's rays.dat)
+void put_ld(FILE *fh, double x) {
+    char buf[64];
+    const double ax = std::fabs(x);
+    if (x == 0.0) {
+        snprintf(buf, sizeof buf, "0.0000000000000000");
+    } else if (ax >= 0.1 && ax < 1e17) {
+        const int e10 = (int)std::floor(std::log10(ax));
+        int dec = e10 < 0 ? 17 : 16 - e10;
+        if (dec < 0) dec = 0;
+        snprintf(buf, sizeof buf, "%.*f", dec, x);
+    } else if (std::isfinite(x)) {
+        const int e10 = (int)std::floor(std::log10(ax));
+        snprintf(buf, sizeof buf, "%.16fE%+04d", x / std::pow(10.0, e10), e10);
+        fprintf(fh, "%26s", buf);
+        return;
+    } else {
+        snprintf(buf, sizeof buf, "%s", std::isnan(x) ? "NaN" : (x > 0 ? "Infinity" : "-Infinity"));
+    }
+    fprintf(fh, "%21s     ", buf);
+}
+
+// keep_delta > 0: rewrite ./rays.dat from the converged ray parameters
+// (subroutineR-quiet.f90:98-105,157-164,432-433).  Formatting of results, host side.
+void write_rays_dat(const double *vels, const double *depths, int NL, const double *off,
+                    const double *dep, int nsrc, const double *p) {
+    FILE *fh = fopen("rays.dat", "w");
+    if (!fh) return;
+    std::vector<double> H((size_t)NL + 2);
+    for (int k = 0; k < nsrc; ++k) {
+        int    inN = 0;
+        double diff = 0.0;
+        for (int i = 1; i <= NL; ++i) { inN = i; diff = depths[i - 1] - dep[k]; if (diff > 0.0) break; }
+        const int nl = NL <= 0 ? 1 : (diff < 0.0 ? NL + 1 : inN);
+        if (nl == 1) {
+            put_ld(fh, off[k]); fputc('\n', fh);
+            put_ld(fh, dep[k]); fputc('\n', fh);
+            continue;
+        }
+        H[0] = depths[0];
+        for (int i = 1; i < nl - 1; ++i) H[i] = depths[i] - depths[i - 1];
+        H[nl - 1] = dep[k] - depths[nl - 2];
+        for (int i = 0; i < nl; ++i) {
+            volatile double pv = (p[k] * p[k]) * (vels[i] * vels[i]);
+            volatile double cosv = std::sqrt(1.0 - pv);
+            volatile double q = H[i] / cosv;
+            volatile double q2 = q * q, h2 = H[i] * H[i];
+            put_ld(fh, std::sqrt(q2 - h2));
+        }
+        fputc('\n', fh);
+        for (int i = 0; i < nl; ++i) put_ld(fh, H[i]);
+        fputc('\n', fh);
+    }
+    fclose(fh);
+}
+
+void dff_impl(const double *vels, const double *depths, int NL, const double *off,
+              const double *dep, int nsrc, double *timeP, int keep_delta) {
+    if (nsrc <= 0) return;
+    std::vector<double> p;
+    if (keep_delta > 0) p.resize((size_t)nsrc);
+    HostCall h{};
+    h.vels = vels; h.depths = depths; h.nlayers = &NL;
+    h.B = 1; h.ldv = std::max(NL, 0) + 1; h.ldz = std::max(NL, 0); h.kmode = 0;
+    h.off = off; h.dep = dep; h.nsrc = nsrc;
+    h.timeP = timeP; h.p_out = keep_delta > 0 ? p.data() : nullptr;
+    if (run_host(h) != 0) {
+        nan_fill(timeP, (size_t)nsrc);
+        complain();
+        return;
+    }
+    if (keep_delta > 0) write_rays_dat(vels, depths, NL, off, dep, nsrc, p.data());
+}
+
+}  // namespace
+
+extern "C" {
+
+#ifdef RTB200_DFF_IS_7ARG
+#define RTB200_DFF8 dff8_
+#define RTB200_DFF7 dff_
+#else
+#define RTB200_DFF8 dff_
+#define RTB200_DFF7 dff7_
+#endif
+
+void RTB200_DFF8(const double *vels, const double *depths, const int *NLayers,
+                 const double *src_offset, const double *src_depth, const int *NSrc,
+                 double *timeP, const int *keep_delta) {
+    dff_impl(vels, depths, *NLayers, src_offset, src_depth, *NSrc, timeP,
+             keep_delta ? *keep_delta : -1);
+}
+
+void RTB200_DFF7(const double *vels, const double *depths, const int *NLayers,
+                 const double *src_offset, const double *src_depth, const int *NSrc,
+                 double *timeP) {
+    dff_impl(vels, depths, *NLayers, src_offset, src_depth, *NSrc, timeP, -1);
+}
+
+void tracerays_(const double *vels, const double *depths, const int *NLayers,
+                const double *src_offset, const double *src_depth, const int *NSrc,
+                double *timeP, const int *keep_delta) {
+    dff_impl(vels, depths, *NLayers, src_offset, src_depth, *NSrc, timeP,
+             keep_delta ? *keep_delta : -1);
+}
+
+int dff_batch(const double *vels, const double *depths, const int *nlayers, const int *B,
+              const int *ldv, const int *ldz, const double *src_offset, const double *src_depth,
+              const int *NSrc, double *timeP, const double *tobs, const double *sigma,
+              double *logL, double *p_out) {
+    HostCall h{};
+    h.vels = vels; h.depths = depths; h.nlayers = nlayers;
+    h.B = *B; h.ldv = *ldv; h.ldz = *ldz; h.kmode = 0;
+    h.off = src_offset; h.dep = src_depth; h.nsrc = *NSrc;
+    h.timeP = timeP; h.tobs = tobs; h.sigma = sigma; h.logL = logL; h.p_out = p_out;
+    return run_host(h);
+}
+
+int loglhood_batch(const int *k, const double *vp, const double *ziface, const int *B,
+                   const int *ldv, const int *ldz, const double *src_offset,
+                   const double *src_depth, const int *NSrc, const double *tobs,
+                   const double *sigma, double *logL, double *tpred) {
+    HostCall h{};
+    h.vels = vp; h.depths = ziface; h.nlayers = k;
+    h.B = *B; h.ldv = *ldv; h.ldz = *ldz; h.kmode = 1;
+    h.off = src_offset; h.dep = src_depth; h.nsrc = *NSrc;
+    h.timeP = tpred; h.tobs = tobs; h.sigma = sigma; h.logL = logL; h.p_out = nullptr;
+    return run_host(h);
+}
+
+int rtb200_dff_batch_device(const double *d_vels, const double *d_depths, const int *d_nlayers,
+                            int B, int ldv, int ldz, const double *d_src_offset,
+                            const double *d_src_depth, int NSrc, double *d_timeP,
+                            const double *d_tobs, const double *d_sigma, double *d_logL,
+                            double *d_p_out, int kmode, void *stream) {
+    if (int rc = ensure_init()) return rc;
+    g.err.clear();
+    if (B <= 0 || NSrc <= 0) return 0;
+    if (d_logL && (!d_tobs || !d_sigma)) return fail("logL needs tobs and sigma");
+    cudaStream_t st = stream ? (cudaStream_t)stream : g.s_comp;
+    TileCfg cfg;
+    const bool al = aligned16(d_vels) && aligned16(d_depths);
+    if (int rc = choose_cfg(B, ldv, std::max(ldz, 0), NSrc, al, cfg)) return rc;
+    CK(g.cosv.reserve((size_t)NSrc * 8));
+    CK(rtb::launch_prep_sources(d_src_offset, d_src_depth, g.cosv.as<double>(), NSrc, st));
+    BatchArgs a{};
+    a.vels = d_vels; a.depths = d_depths; a.nlayers = d_nlayers;
+    a.B = B; a.ldv = ldv; a.ldz = std::max(ldz, 0); a.kmode = kmode;
+    a.src_offset = d_src_offset; a.src_depth = d_src_depth; a.src_cos = g.cosv.as<double>();
+    a.tobs = d_tobs; a.nsrc = NSrc; a.sigma = d_sigma;
+    a.timeP = d_timeP; a.p_out = d_p_out; a.logL = d_logL;
+    a.logc = d_logL ? log_norm_const(NSrc) : 0.0;
+    CK(cudaEventRecord(g.ev_k0[0], st));
+    CK(rtb::launch_batch(a, cfg, st));
+    CK(cudaEventRecord(g.ev_k1[0], st));
+    g.launches += 2;
+    g.last = cfg;
+    if (!stream) {
+        CK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, g.ev_k0[0], g.ev_k1[0]));
+        g.kernel_ms = g.total_ms = ms;
+    }
+    return 0;
+}
+
+int rtb200_init(int device) { return ensure_init(device); }
+
+void rtb200_shutdown(void) {
+    if (!g.inited || !g.ok) { g.inited = false; return; }
+    cudaSetDevice(g.device);
+    cudaDeviceSynchronize();
+    for (DevBuf *b : {&g.vels, &g.depths, &g.nl, &g.off, &g.dep, &g.cosv, &g.tobs, &g.sigma,
+                      &g.timeP, &g.pout, &g.logL})
+        b->release();
+    for (int i = 0; i < kMaxChunks; ++i) {
+        cudaEventDestroy(g.ev_h2d[i]);
+        cudaEventDestroy(g.ev_k0[i]);
+        cudaEventDestroy(g.ev_k1[i]);
+    }
+    cudaEventDestroy(g.ev_t0);
+    cudaEventDestroy(g.ev_t1);
+    cudaStreamDestroy(g.s_comp);
+    cudaStreamDestroy(g.s_h2d);
+    cudaStreamDestroy(g.s_d2h);
+    g.inited = g.ok = false;
+}
+
+const char *rtb200_last_error(void) { return g.err.c_str(); }
+
+int rtb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int rtb200_set_option(const char *name, double value) {
+    const int v = (int)value;
+    if (!strcmp(name, "variant")) g.opt_variant = v < 0 ? 1 : v;
+    else if (!strcmp(name, "threads")) g.opt_threads = v;
+    else if (!strcmp(name, "tile_models")) g.opt_tile_models = v > 0 ? even_up(v) : 0;
+    else if (!strcmp(name, "tile_sources")) g.opt_tile_sources = v;
+    else if (!strcmp(name, "chunk_models")) g.opt_chunk_models = v;
+    else if (!strcmp(name, "ctas_per_sm")) g.opt_ctas = v;
+    else return -1;
+    return 0;
+}
+
+double rtb200_get_stat(const char *name) {
+    if (!strcmp(name, "kernel_ms")) return g.kernel_ms;
+    if (!strcmp(name, "total_ms")) return g.total_ms;
+    if (!strcmp(name, "launches")) return (double)g.launches;
+    if (!strcmp(name, "tile_models")) return g.last.M;
+    if (!strcmp(name, "tile_sources")) return g.last.SC;
+    if (!strcmp(name, "smem_bytes")) return (double)g.last.smem;
+    if (!strcmp(name, "grid")) return g.last.grid;
+    if (!strcmp(name, "threads")) return g.last.threads;
+    if (!strcmp(name, "ctas_per_sm")) return g.last_ctas;
+    if (!strcmp(name, "variant")) return g.last.variant;
+    if (!strcmp(name, "sms")) return g.sms;
+    return std::numeric_limits<double>::quiet_NaN();
+}
+
+double rtb200_fp64_peak_tflops(int repeats) {
+    if (ensure_init()) return std::numeric_limits<double>::quiet_NaN();
+    double tf = 0.0;
+    if (rtb::fp64_peak(&tf, repeats, g.s_comp) != cudaSuccess)
+        return std::numeric_limits<double>::quiet_NaN();
+    g.launches += 1 + (repeats > 0 ? repeats : 3);
+    return tf;
+}
+
+void rtb200_shard_range(long long B, int rank, int world, long long *lo, long long *hi) {
+    if (world < 1) world = 1;
+    const long long q = B / world, r = B % world;
+    *lo = rank * q + std::min<long long>(rank, r);
+    *hi = *lo + q + (rank < r ? 1 : 0);
+}
+
+}  // extern "C"

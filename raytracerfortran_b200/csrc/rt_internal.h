@@ -1,0 +1,59 @@
+// rt_internal.h -- shared between the kernels (rt_kernels.cu) and the C ABI (rt_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rtb {
+
+// Solver constants of the reference (subroutineR-quiet.f90).
+constexpr double kTol          = 1.0e-1;   // :234, :351   tol = 1.d-1
+constexpr int    kNewtonMaxIt  = 15;       // :233
+constexpr int    kBisectMaxIt  = 20;       // :346
+constexpr double kClampRR      = 1.0e-9;   // :250
+constexpr double kSafeEps      = 1.0e-10;  // :142, :388
+constexpr double kBisectLo     = 1.0e-10;  // :148
+constexpr double kBisectHiEps  = 1.0e-12;  // :148
+constexpr int    kHalveCap     = 2200;     // the reference never terminates on a NaN p0 (:125-133)
+constexpr double kFakeIface    = 9999.9;   // loglhood.f90:141
+
+// One batched launch.  Every pointer is a device pointer.
+struct BatchArgs {
+    const double *vels;        // [B][ldv]
+    const double *depths;      // [B][ldz]
+    const int    *nlayers;     // [B]; kmode: node counts k
+    int           B, ldv, ldz;
+    int           kmode;       // LOGLHOOD_RT model mapping (loglhood.f90:127-146)
+    const double *src_offset;  // [nsrc]
+    const double *src_depth;   // [nsrc]
+    const double *src_cos;     // [nsrc]  depth / sqrt(offset^2 + depth^2), from prep_sources
+    const double *tobs;        // [nsrc] or null
+    int           nsrc;
+    const double *sigma;       // [B] or null
+    double       *timeP;       // [B][nsrc] or null
+    double       *p_out;       // [B][nsrc] or null
+    double       *logL;        // [B] or null
+    double        logc;        // log(1/(2 pi)^(N/2)), computed once on the host
+    int           padded;      // vels/depths are readable up to a whole number of tiles
+};
+
+// Tile geometry chosen by the host for one launch.
+struct TileCfg {
+    int M;        // models per tile (even)
+    int SC;       // sources per chunk
+    int LP;       // per-model row length of the derived tables (odd, >= max velocities)
+    int TS;       // row stride of the travel-time tile (odd)
+    int threads;  // CTA size
+    int grid;     // persistent CTAs
+    int variant;  // 0: lock-step loops, 1: lane state machine with refill
+    int use_tma;  // rows are 16-byte aligned: stage with cp.async.bulk
+    size_t smem;  // dynamic shared memory bytes
+};
+
+size_t      tile_smem_bytes(const TileCfg &c, int ldv, int ldz);
+cudaError_t launch_prep_sources(const double *off, const double *dep, double *cosv, int nsrc,
+                                cudaStream_t st);
+cudaError_t launch_batch(const BatchArgs &a, const TileCfg &c, cudaStream_t st);
+int         max_ctas_per_sm(const TileCfg &c);   // occupancy of the batch kernel for this geometry
+cudaError_t fp64_peak(double *tflops, int repeats, cudaStream_t st);
+
+}  // namespace rtb
