@@ -120,8 +120,9 @@ def test_near_critical_50_layers(variant):
     got = rt.dff_batch(v, z, nl, so, sd, want_p=True)
     assert_bitexact(got["timeP"], ref["timeP"], "timeP")
     assert_bitexact(got["p"], ref["p"], "p")
-    st = oracle.batch_stats(v[:8], z[:8], nl[:8], so, sd)
-    assert st["bisect"] > 0.9 * (st["rays"] - st["top"]) and st["n_clamp"] > 0
+    st = oracle.batch_stats(v, z, nl, so, sd)
+    assert st["bisect"] > 0.9 * (st["rays"] - st["top"])       # the workload is what it claims to be
+    assert st["sum_nl"] / st["rays"] > 20
 
 
 def test_transdimensional_loglhood_batch():
@@ -233,7 +234,7 @@ def test_config2_full_size_properties():
     """1M models x 64 sources (BASELINE.json configs[1]).  The oracle cannot sweep 64M rays in
     seconds, so: (a) a random sample of models is checked bit-exactly against the oracle,
     (b) batch invariance: the same models evaluated alone give the same bits, (c) physical
-    sanity of every ray: T >= straight-line time at the fastest velocity, 0 < p < 1/vmin."""
+    sanity of every ray: T >= depth / fastest velocity, 0 < p < 1/vmin."""
     cfg = workloads.CONFIGS["config2"]
     B, nlayers, nsrc = cfg["B"], cfg["nlayers"], cfg["nsrc"]
     v, z, nl = workloads.make_models(B, nlayers, cfg["seed"])
@@ -253,7 +254,9 @@ def test_config2_full_size_properties():
     assert_bitexact(again["logL"], LL[pick], "batch invariance logL")
     conv = T != -999.0
     assert conv.mean() > 0.999
-    straight = np.sqrt(so * so + sd * sd)[None, :] / v.max(axis=1)[:, None]
-    assert np.all(T[conv] >= straight[conv] * (1 - 1e-4))   # the solver stops within 0.1 m of the offset
+    # sum h/(v cos) >= depth / vmax at ANY p (the solver's quirky `conv` flag lets a ray that used
+    # all 15 Newton updates return the time of whatever p it ended on -- SURVEY.md hazard list)
+    vertical = sd[None, :] / v.max(axis=1)[:, None]
+    assert np.all(T[conv] >= vertical[conv] * (1 - 1e-12))
     assert np.all(P > 0) and np.all(P < 1.0 / 1500.0)
     assert np.all(np.isfinite(LL))
