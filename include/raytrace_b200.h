@@ -115,6 +115,10 @@ int         rtb200_set_option(const char *name, double value);
 double      rtb200_get_stat(const char *name);
 /* sustained FP64 FMA throughput of the current device in TFLOP/s (roofline denominator) */
 double      rtb200_fp64_peak_tflops(int repeats);
+/* Self-test of the hot loop's rsqrt-seeded square root and divisions: draws `samples` operand
+ * triples over the solver's range and compares them bit for bit with CUDA's correctly rounded
+ * sqrt and divide.  Returns the number of mismatching results (0 expected), -1 on failure. */
+double      rtb200_selftest_fast_division(double samples, unsigned long long seed);
 /* contiguous slice [*lo, *hi) of B models owned by `rank` of `world` (model-axis sharding) */
 void        rtb200_shard_range(long long B, int rank, int world, long long *lo, long long *hi);
 

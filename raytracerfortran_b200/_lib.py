@@ -14,6 +14,7 @@ EXPORTS = (
     "dff_", "dff7_", "tracerays_", "dff_batch", "loglhood_batch", "rtb200_dff_batch_device",
     "rtb200_init", "rtb200_shutdown", "rtb200_last_error", "rtb200_device_count",
     "rtb200_set_option", "rtb200_get_stat", "rtb200_fp64_peak_tflops", "rtb200_shard_range",
+    "rtb200_selftest_fast_division",
 )
 
 _lib = None
@@ -57,6 +58,8 @@ def load():
     lib.rtb200_get_stat.argtypes = [C.c_char_p]
     lib.rtb200_fp64_peak_tflops.restype = d
     lib.rtb200_fp64_peak_tflops.argtypes = [i]
+    lib.rtb200_selftest_fast_division.restype = d
+    lib.rtb200_selftest_fast_division.argtypes = [d, C.c_ulonglong]
     lib.rtb200_shard_range.restype = None
     lib.rtb200_shard_range.argtypes = [C.c_longlong, i, i, C.POINTER(C.c_longlong),
                                        C.POINTER(C.c_longlong)]

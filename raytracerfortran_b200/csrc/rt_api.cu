@@ -542,6 +542,14 @@ double rtb200_fp64_peak_tflops(int repeats) {
     return tf;
 }
 
+double rtb200_selftest_fast_division(double samples, unsigned long long seed) {
+    if (ensure_init()) return -1.0;
+    double bad = -1.0;
+    if (rtb::fastpath_selftest(samples, seed, &bad, g.s_comp) != cudaSuccess) return -1.0;
+    g.launches += 1;
+    return bad;
+}
+
 void rtb200_shard_range(long long B, int rank, int world, long long *lo, long long *hi) {
     if (world < 1) world = 1;
     const long long q = B / world, r = B % world;

@@ -55,5 +55,7 @@ cudaError_t launch_prep_sources(const double *off, const double *dep, double *co
 cudaError_t launch_batch(const BatchArgs &a, const TileCfg &c, cudaStream_t st);
 int         max_ctas_per_sm(const TileCfg &c);   // occupancy of the batch kernel for this geometry
 cudaError_t fp64_peak(double *tflops, int repeats, cudaStream_t st);
+cudaError_t fastpath_selftest(double samples, unsigned long long seed, double *mismatches,
+                              cudaStream_t st);
 
 }  // namespace rtb

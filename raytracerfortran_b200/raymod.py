@@ -133,6 +133,14 @@ def fp64_peak_tflops(repeats=3):
     return v
 
 
+def selftest_fast_division(samples=1e9, seed=1):
+    """Mismatches between the hot loop's rsqrt-seeded sqrt/divisions and CUDA's built-ins."""
+    bad = _lib.load().rtb200_selftest_fast_division(float(samples), int(seed))
+    if bad < 0:
+        _lib.check(-1)
+    return int(bad)
+
+
 def shard_range(B, rank, world):
     lo, hi = C.c_longlong(), C.c_longlong()
     _lib.load().rtb200_shard_range(int(B), int(rank), int(world), C.byref(lo), C.byref(hi))

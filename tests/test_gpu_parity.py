@@ -153,6 +153,12 @@ def test_loglhood_overflowing_normaliser_is_minus_inf_like_the_reference():
     assert np.all(np.isneginf(ref["logL"])) and np.array_equal(got["logL"], ref["logL"])
 
 
+def test_fast_division_matches_builtin():
+    """The hot loop's rsqrt-seeded sqrt and divisions vs CUDA's correctly rounded built-ins,
+    bit for bit, on 3e9 operand triples spanning the solver's range (near-critical included)."""
+    assert rt.selftest_fast_division(3e9, seed=12345) == 0
+
+
 # ---------------------------------------------------------------------------------------------
 # edge cases
 # ---------------------------------------------------------------------------------------------
