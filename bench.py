@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--models", type=int, default=0, help="override models per GPU (debug only)")
     ap.add_argument("--variant", type=int, default=-1, help="kernel variant (debug only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (debug only)")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (debug only)")
     return ap.parse_args()
 
 
@@ -187,6 +188,9 @@ def main():
     os.environ["RTB200_DEVICE"] = str(local)
     if args.variant >= 0:
         rt.set_option("variant", args.variant)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        rt.set_option(name, float(val))
 
     cfg, v, z, nl, so, sd = workload(rank, args.models)
     B, S = len(v), len(so)
