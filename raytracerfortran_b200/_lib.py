@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libraytrace_b200.so")
+# RTB200_LIB lets profiling scripts load an experimental build of the same library
+LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "libraytrace_b200.so")
 
 # every symbol include/raytrace_b200.h declares
 EXPORTS = (

@@ -33,15 +33,17 @@ def stale():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build_library(force=False, verbose=False):
-    """Build (if stale) and return the path of the shared library."""
-    if force or stale():
-        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+def build_library(force=False, verbose=False, out=None, defines=()):
+    """Build (if stale) and return the path of the shared library.  `out` / `defines` build an
+    experimental copy (profiling A/B runs) without touching the product library."""
+    if out is not None or force or stale():
+        cmd = [nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] \
+            + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or LIB] + SOURCES
         env = dict(os.environ)
         env.pop("CC", None)
         env.pop("CXX", None)
         subprocess.check_call(cmd, env=env)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -149,7 +149,7 @@ int choose_cfg(int B, int ldv, int ldz, int nsrc, bool aligned, TileCfg &c) {
     for (;;) {
         c.M = M;
         c.smem = rtb::tile_smem_bytes(c, ldv, ldz);
-        const bool fits = c.smem <= per_cta && (size_t)M * c.SC <= 65536 &&
+        const bool fits = c.smem <= per_cta && (size_t)M * c.SC <= 65536 && M <= 2048 && c.SC <= 4096 &&
                           (size_t)M * (ldv + ldz) * 8 < (1u << 20);
         if (fits) break;
         if (M > 2) { M = std::max(2, even_up(M / 2)); continue; }
