@@ -1,0 +1,85 @@
+"""GPU parity on the shapes of BASELINE.json configs 3, 4 and 5 (config 1 and 2 are in
+test_gpu_parity.py).  Where the full configuration is too large for the oracle, a slice of the
+models is compared bit for bit and the rest through batch invariance."""
+import numpy as np
+import pytest
+
+import oracle
+import raytracerfortran_b200 as rt
+from raytracerfortran_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def logl_close(got, want, nsrc, sigma):
+    scale = np.maximum(np.maximum(np.abs(want), nsrc * np.abs(np.log(sigma))), 1.0)
+    return np.all(np.abs(got - want) <= 1e-12 * scale)
+
+
+def test_config3_transdimensional_step():
+    """4096 models/step, k = 1..30 (truncated Poisson, lambda 3.01), 256 sources, logL fused."""
+    cfg = workloads.CONFIGS["config3"]
+    B, nsrc = cfg["B"], cfg["nsrc"]
+    k, vp, zi = workloads.make_transd_models(B, cfg["kmax"], cfg["seed"])
+    so, sd = workloads.make_sources(nsrc, cfg["seed"])
+    t0 = oracle.loglhood_rt(vp[0, :k[0]], zi[0, :max(k[0] - 1, 0)], so, sd, np.zeros(nsrc), 1.0)[1]
+    tobs, sigma = workloads.make_observations(t0, B, cfg["seed"])
+    ll, pred = rt.loglhood_batch(k, vp, zi, so, sd, tobs, sigma, want_pred=True)
+    pick = np.arange(0, B, 9)
+    for b in pick:
+        w_ll, w_pred = oracle.loglhood_rt(vp[b, :k[b]], zi[b, :max(k[b] - 1, 0)], so, sd, tobs, sigma[b])
+        assert np.array_equal(bits(pred[b]), bits(w_pred))
+        assert logl_close(np.array([ll[b]]), np.array([w_ll]), nsrc, sigma[b:b + 1])
+    assert np.all(np.isfinite(ll))
+    assert (k == 1).any() and (k > 8).any()
+
+
+def test_config4_replicas_on_one_rank():
+    """One rank's share of config 4: 8 replicas x 1024 proposals x 256 sources, evaluated on
+    device-resident tensors in one launch, then one (single-rank) swap round."""
+    import torch
+    from raytracerfortran_b200 import tempering
+    cfg = workloads.CONFIGS["config4"]
+    R, P, nsrc, kmax = 8, cfg["proposals"], cfg["nsrc"], cfg["kmax"]
+    k, vp, zi = workloads.make_transd_models(R * P, kmax, cfg["seed"])
+    so, sd = workloads.make_sources(nsrc, cfg["seed"])
+    t0 = oracle.loglhood_rt(vp[1, :k[1]], zi[1, :max(k[1] - 1, 0)], so, sd, np.zeros(nsrc), 1.0)[1]
+    tobs, sigma = workloads.make_observations(t0, R * P, cfg["seed"])
+    dev = torch.device("cuda:0")
+    f = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    ll = tempering.evaluate_replicas(f(k).reshape(R, P), f(vp).reshape(R, P, kmax),
+                                     f(zi).reshape(R, P, kmax - 1), f(so), f(sd), f(tobs),
+                                     f(sigma).reshape(R, P))
+    torch.cuda.synchronize()
+    ll = ll.cpu().numpy().reshape(-1)
+    for b in range(0, R * P, 37):
+        w_ll, _ = oracle.loglhood_rt(vp[b, :k[b]], zi[b, :max(k[b] - 1, 0)], so, sd, tobs, sigma[b])
+        assert logl_close(np.array([ll[b]]), np.array([w_ll]), nsrc, sigma[b:b + 1])
+    # the replicas' current states: best proposal of each; one swap round on a single rank
+    cur = torch.from_numpy(ll.reshape(R, P).max(axis=1).copy())
+    beta = torch.from_numpy(tempering.temperature_ladder(R, 1.4))
+    new_beta, st = tempering.tempering_swap_round(cur, beta, seed=4, round_index=0)
+    assert sorted(new_beta.tolist()) == sorted(beta.tolist()) and st["bytes_per_rank"] == 16 * R
+
+
+def test_config5_stress_slice():
+    """config-5 shape at reduced model count: 50 interfaces, 1024 near-critical sources
+    (4 source chunks per tile), logL fused and no travel-time store."""
+    cfg = workloads.CONFIGS["config5"]
+    B, nsrc = 600, cfg["nsrc"]
+    v, z, nl = workloads.make_models(B, cfg["nlayers"], cfg["seed"], min_thickness=False)
+    so, sd = workloads.make_sources(nsrc, cfg["seed"], near_critical=True)
+    tobs, sigma = workloads.make_observations(np.full(nsrc, 2.0), B, cfg["seed"])
+    got = rt.dff_batch(v, z, nl, so, sd, tobs=tobs, sigma=sigma, want_times=True, want_p=True)
+    pick = np.arange(0, B, 25)
+    ref = oracle.dff_batch(v[pick], z[pick], nl[pick], so, sd, tobs=tobs, sigma=sigma[pick], want_p=True)
+    assert np.array_equal(bits(got["timeP"][pick]), bits(ref["timeP"]))
+    assert np.array_equal(bits(got["p"][pick]), bits(ref["p"]))
+    # N = 1024 overflows the reference's normaliser: logL = -inf on both sides (loglhood.f90:194)
+    assert np.array_equal(got["logL"][pick], ref["logL"])
+    only_ll = rt.dff_batch(v, z, nl, so, sd, tobs=tobs, sigma=sigma, want_times=False)
+    assert np.array_equal(only_ll["logL"], got["logL"])

@@ -1,0 +1,90 @@
+"""Multi-rank logic on CPU: model-axis sharding and the parallel-tempering swap all-gather,
+world_size 2 over gloo (the GPU path uses the same code over NCCL)."""
+import math
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from raytracerfortran_b200 import tempering
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_swap_rule_matches_tempswp_mh():
+    """prjmh_temper_rf.f90:1341-1344: logratio = (beta2-beta1)*(logL1-logL2); accept if u <= exp(.)."""
+    rng = np.random.default_rng(3)
+    logL = rng.normal(-50, 30, 64)
+    beta = tempering.temperature_ladder(64, 1.4)
+    for rnd in range(20):
+        pairs, acc = tempering.swap_decisions(logL, beta, seed=99, round_index=rnd)
+        pairs2, u = tempering.swap_pairs(64, 99, rnd)
+        assert np.array_equal(pairs, pairs2)
+        assert sorted(pairs.ravel().tolist()) == list(range(64))       # a perfect matching
+        for (i, j), a, uu in zip(pairs, acc, u):
+            logratio = (beta[j] - beta[i]) * (logL[i] - logL[j])
+            want = uu <= (math.exp(logratio) if logratio < 700 else math.inf)
+            assert bool(a) == want
+        new = tempering.apply_swaps(beta, pairs, acc)
+        assert sorted(new.tolist()) == sorted(beta.tolist())           # betas are permuted, never lost
+    # a colder chain always takes the better state: beta_j > beta_i and logL_i > logL_j => accept
+    p, a = tempering.swap_decisions([0.0, -1000.0], [0.1, 1.0], 1, 0)
+    i, j = p[0]
+    assert bool(a[0]) == ((np.array([0.1, 1.0])[j] - np.array([0.1, 1.0])[i])
+                          * (np.array([0.0, -1000.0])[i] - np.array([0.0, -1000.0])[j]) >= 0 or not a[0])
+
+
+def test_temperature_ladder():
+    b = tempering.temperature_ladder(6, 1.4, n_cold=2)
+    assert b[0] == b[1] == 1.0 and np.allclose(b[2:], 1.0 / 1.4 ** np.arange(1, 5))
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_local, seed = 4, 2024
+        rng = np.random.default_rng(100)                    # same stream on both ranks
+        logL_all = rng.normal(-40, 25, world * n_local)
+        beta_all = tempering.temperature_ladder(world * n_local, 1.4)
+        lo, hi = tempering.shard_range(world * n_local, rank, world)
+        assert (lo, hi) == (rank * n_local, (rank + 1) * n_local)
+        logL = torch.from_numpy(logL_all[lo:hi].copy())
+        beta = torch.from_numpy(beta_all[lo:hi].copy())
+        g_l, g_b = tempering.allgather_replicas(logL, beta)
+        assert np.array_equal(g_l, logL_all) and np.array_equal(g_b, beta_all)
+        history = []
+        for rnd in range(5):
+            beta, st = tempering.tempering_swap_round(logL, beta, seed, rnd)
+            history.append((beta.numpy().copy(), st["accept"].copy(), st["pairs"].copy()))
+        ret[rank] = history
+    finally:
+        dist.destroy_process_group()
+
+
+def test_swap_round_world_size_2_gloo():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    h0, h1 = ret[0], ret[1]
+    # serial restatement of the same five rounds
+    rng = np.random.default_rng(100)
+    logL_all = rng.normal(-40, 25, 8)
+    beta_all = tempering.temperature_ladder(8, 1.4)
+    for rnd in range(5):
+        pairs, acc = tempering.swap_decisions(logL_all, beta_all, 2024, rnd)
+        beta_all = tempering.apply_swaps(beta_all, pairs, acc)
+        assert np.array_equal(h0[rnd][1], acc) and np.array_equal(h1[rnd][1], acc)     # same decisions
+        assert np.array_equal(h0[rnd][2], pairs) and np.array_equal(h1[rnd][2], pairs)
+        assert np.array_equal(np.concatenate([h0[rnd][0], h1[rnd][0]]), beta_all)      # same ladder
+    assert sum(int(h0[r][1].sum()) for r in range(5)) > 0                              # something swapped
