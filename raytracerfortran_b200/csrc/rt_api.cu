@@ -52,7 +52,9 @@ struct Ctx {
     cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t  ev_h2d[kMaxChunks], ev_k0[kMaxChunks], ev_k1[kMaxChunks];
     cudaEvent_t  ev_t0 = nullptr, ev_t1 = nullptr;
-    DevBuf vels, depths, nl, off, dep, cosv, tobs, sigma, timeP, pout, logL;
+    DevBuf vels, depths, nl, off, dep, cosv, tobs, sigma, timeP, pout, logL, arena;
+    void  *pin = nullptr;          // pinned staging for small calls
+    size_t pin_cap = 0;
     // options (<= 0: automatic)
     int opt_variant = 1, opt_threads = 0, opt_tile_models = 0, opt_tile_sources = 0,
         opt_chunk_models = 0, opt_ctas = 0;
@@ -194,6 +196,79 @@ struct HostCall {
     double *logL, *p_out;
 };
 
+// Small calls (the one-model dff_ of R's .Fortran, a handful of proposals): everything goes
+// through one pinned staging buffer -- one H2D copy, one launch (cos_t computed in the kernel),
+// one D2H copy, one stream -- because here the call is latency, not throughput.
+constexpr size_t kSmallBytes = 256 * 1024;
+
+int run_host_small(const HostCall &h, const TileCfg &cfg, int ldz) {
+    const size_t B = (size_t)h.B, S = (size_t)h.nsrc, M = (size_t)cfg.M;
+    const size_t Bpad = (B + M - 1) / M * M;
+    auto up = [](size_t x) { return (x + 15) / 16 * 16; };
+    size_t o = 0;
+    const size_t o_v = o;   o += up(Bpad * h.ldv * 8);
+    const size_t o_z = o;   o += up(Bpad * std::max(ldz, 1) * 8);
+    const size_t o_off = o; o += up(S * 8);
+    const size_t o_dep = o; o += up(S * 8);
+    const size_t o_obs = o; o += up(S * 8);
+    const size_t o_sig = o; o += up(B * 8);
+    const size_t o_nl = o;  o += up(Bpad * 4);
+    const size_t in_bytes = o;
+    const size_t o_t = o;   o += h.timeP ? up(B * S * 8) : 0;
+    const size_t o_p = o;   o += h.p_out ? up(B * S * 8) : 0;
+    const size_t o_l = o;   o += h.logL ? up(B * 8) : 0;
+    const size_t total = o;
+    if (total > g.pin_cap) {
+        if (g.pin) cudaFreeHost(g.pin);
+        g.pin = nullptr; g.pin_cap = 0;
+        CK(cudaMallocHost(&g.pin, 2 * total + 4096));
+        g.pin_cap = 2 * total + 4096;
+    }
+    CK(g.arena.reserve(total));
+    char *hp = static_cast<char *>(g.pin), *dp = g.arena.as<char>();
+    memset(hp + o_v, 0, o_off - o_v);
+    for (size_t b = 0; b < B; ++b) memcpy(hp + o_v + b * h.ldv * 8, h.vels + b * h.ldv, (size_t)h.ldv * 8);
+    if (ldz > 0) memcpy(hp + o_z, h.depths, B * ldz * 8);
+    memcpy(hp + o_off, h.off, S * 8);
+    memcpy(hp + o_dep, h.dep, S * 8);
+    if (h.tobs) memcpy(hp + o_obs, h.tobs, S * 8);
+    if (h.sigma) memcpy(hp + o_sig, h.sigma, B * 8);
+    memset(hp + o_nl, 0, Bpad * 4);
+    memcpy(hp + o_nl, h.nlayers, B * 4);
+    cudaStream_t st = g.s_comp;
+    CK(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st));
+    BatchArgs a{};
+    a.vels = reinterpret_cast<double *>(dp + o_v);
+    a.depths = reinterpret_cast<double *>(dp + o_z);
+    a.nlayers = reinterpret_cast<int *>(dp + o_nl);
+    a.B = h.B; a.ldv = h.ldv; a.ldz = ldz; a.kmode = h.kmode;
+    a.src_offset = reinterpret_cast<double *>(dp + o_off);
+    a.src_depth = reinterpret_cast<double *>(dp + o_dep);
+    a.src_cos = nullptr;
+    a.tobs = h.tobs ? reinterpret_cast<double *>(dp + o_obs) : nullptr;
+    a.nsrc = h.nsrc;
+    a.sigma = h.sigma ? reinterpret_cast<double *>(dp + o_sig) : nullptr;
+    a.timeP = h.timeP ? reinterpret_cast<double *>(dp + o_t) : nullptr;
+    a.p_out = h.p_out ? reinterpret_cast<double *>(dp + o_p) : nullptr;
+    a.logL = h.logL ? reinterpret_cast<double *>(dp + o_l) : nullptr;
+    a.logc = h.logL ? log_norm_const(h.nsrc) : 0.0;
+    a.padded = 1;
+    CK(cudaEventRecord(g.ev_k0[0], st));
+    CK(rtb::launch_batch(a, cfg, st));
+    CK(cudaEventRecord(g.ev_k1[0], st));
+    g.launches++;
+    g.last = cfg;
+    if (total > in_bytes)
+        CK(cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h.timeP) memcpy(h.timeP, hp + o_t, B * S * 8);
+    if (h.p_out) memcpy(h.p_out, hp + o_p, B * S * 8);
+    if (h.logL) memcpy(h.logL, hp + o_l, B * 8);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g.ev_k0[0], g.ev_k1[0]) == cudaSuccess) g.kernel_ms = g.total_ms = ms;
+    return 0;
+}
+
 // Host buffers in, host buffers out: chunked over the model axis so the copy of chunk j+1
 // and the read-back of chunk j-1 overlap the kernel of chunk j.
 int run_host(const HostCall &h) {
@@ -208,6 +283,11 @@ int run_host(const HostCall &h) {
 
     TileCfg cfg;
     if (int rc = choose_cfg(h.B, h.ldv, ldz, h.nsrc, true, cfg)) return rc;
+    {
+        const size_t io = (B * (h.ldv + ldz + 2) + 3 * S) * 8 +
+                          ((h.timeP ? B * S : 0) + (h.p_out ? B * S : 0) + (h.logL ? B : 0)) * 8;
+        if (io <= kSmallBytes) return run_host_small(h, cfg, ldz);
+    }
     // our own buffers are padded to whole tiles, so TMA is always legal on them
     const size_t Bpad = (B + cfg.M - 1) / cfg.M * cfg.M + cfg.M;
     CK(g.vels.reserve(Bpad * h.ldv * 8));
@@ -482,8 +562,11 @@ void rtb200_shutdown(void) {
     if (!g.inited || !g.ok) { g.inited = false; return; }
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
+    if (g.pin) cudaFreeHost(g.pin);
+    g.pin = nullptr;
+    g.pin_cap = 0;
     for (DevBuf *b : {&g.vels, &g.depths, &g.nl, &g.off, &g.dep, &g.cosv, &g.tobs, &g.sigma,
-                      &g.timeP, &g.pout, &g.logL})
+                      &g.timeP, &g.pout, &g.logL, &g.arena})
         b->release();
     for (int i = 0; i < kMaxChunks; ++i) {
         cudaEventDestroy(g.ev_h2d[i]);
