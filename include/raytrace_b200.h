@@ -88,6 +88,17 @@ int loglhood_batch(const int *k, const double *vp, const double *ziface,
                    const double *tobs, const double *sigma,
                    double *logL, double *tpred);
 
+/* INTERPLAYER_novar + LOGLHOOD (loglhood.f90:214-295 then :3-211) over B chain states given as
+ * UNSORTED Voronoi nodes: voro[b][0][i] = depth, voro[b][1][i] = vp of node i (Fortran
+ * voro(ldk, 2, B)), k[b] <= ldk <= 64 nodes.  The nodes are sorted by depth on the device with
+ * the reference's quicksort (quicksort.f90:66-123), ziface(1:k-1) = depth(2:k), and the states
+ * are evaluated as by loglhood_batch.  voro_sorted [B][2][ldk] (or NULL) receives the sorted
+ * nodes, tpred [B][NSrc] (or NULL) DpredRT. */
+int loglhood_batch_voro(const int *k, const double *voro, const int *B, const int *ldk,
+                        const double *src_offset, const double *src_depth, const int *NSrc,
+                        const double *tobs, const double *sigma, double *logL, double *tpred,
+                        double *voro_sorted);
+
 /* ------------------------------------------------------------------------------------------
  * Device-resident entry: every pointer is a CUDA device pointer on the current device and
  * nothing is copied.  Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the

@@ -66,6 +66,8 @@ def lib():
         _lib.orc_dff_batch_faithful.restype = C.c_int
         _lib.orc_dff_batch_faithful.argtypes = [dp, dp, ip, C.c_int, C.c_int, C.c_int, dp, dp,
                                                 C.c_int, dp, C.c_char_p]
+        _lib.orc_loglhood_voro.restype = C.c_double
+        _lib.orc_loglhood_voro.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, dp, C.c_double, dp, dp, dp]
         _lib.orc_batch_stats.restype = None
         _lib.orc_batch_stats.argtypes = [dp, dp, ip, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int,
                                          C.POINTER(Stats)]
@@ -110,6 +112,17 @@ def loglhood_rt(vp, ziface, src_offset, src_depth, tobs, sigma):
     ll = lib().orc_loglhood_rt(v.size, _p(v), _p(z) if z.size else None, _p(so), _p(sd), so.size,
                                _p(ob), float(sigma), _p(pred))
     return ll, pred
+
+
+def loglhood_voro(node_depth, node_vp, src_offset, src_depth, tobs, sigma):
+    """INTERPLAYER_novar + LOGLHOOD_RT on unsorted Voronoi nodes.
+    Returns (logL, DpredRT, sorted_depth, sorted_vp)."""
+    d, v = _d(node_depth), _d(node_vp)
+    so, sd, ob = _d(src_offset), _d(src_depth), _d(tobs)
+    pred, sdp, svp = np.empty(so.size), np.empty(d.size), np.empty(d.size)
+    ll = lib().orc_loglhood_voro(d.size, _p(d), _p(v), _p(so), _p(sd), so.size, _p(ob), float(sigma),
+                                 _p(pred), _p(sdp), _p(svp))
+    return ll, pred, sdp, svp
 
 
 def dff_batch(vels, depths, nlayers, src_offset, src_depth, tobs=None, sigma=None,

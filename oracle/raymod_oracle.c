@@ -447,3 +447,56 @@ void orc_batch_stats(const double *vels, const double *depths, const int *nlayer
     }
     *out = s;
 }
+
+/* ---- "next" row N1: INTERPLAYER_novar (ll:214-295) ---------------------------------- *
+ * Sort the k Voronoi nodes by depth with the reference's own quicksort (Hoare partition,
+ * quicksort.f90:66-123: ties keep the order that algorithm gives them), then
+ * ziface(1:k-1) = depth(2:k) (ll:258-259) and LOGLHOOD_RT on (vp(1:k), ziface).          */
+static void orc_partition2d(double *dep, double *vp, int n, int *marker)
+{
+    double x = dep[0];                                          /* quicksort.f90:93 */
+    int i = 0, j = n + 1;                                       /* 1-based, as in the reference */
+    for (;;) {
+        j = j - 1;
+        while (!(dep[j - 1] <= x)) j = j - 1;                   /* :99-102 */
+        i = i + 1;
+        while (!(dep[i - 1] >= x)) i = i + 1;                   /* :104-107 */
+        if (i < j) {                                            /* :108-115 */
+            double t = dep[i - 1]; dep[i - 1] = dep[j - 1]; dep[j - 1] = t;
+            t = vp[i - 1]; vp[i - 1] = vp[j - 1]; vp[j - 1] = t;
+        } else if (i == j) { *marker = i + 1; return; }         /* :116-118 */
+        else { *marker = i; return; }                           /* :119-121 */
+    }
+}
+
+static void orc_qsortc2d(double *dep, double *vp, int n)
+{
+    if (n > 1) {                                                /* quicksort.f90:71-75 */
+        int iq;
+        orc_partition2d(dep, vp, n, &iq);
+        orc_qsortc2d(dep, vp, iq - 1);
+        orc_qsortc2d(dep + iq - 1, vp + iq - 1, n - iq + 1);
+    }
+}
+
+void orc_interplayer_novar(int k, double *node_depth, double *node_vp)
+{
+    orc_qsortc2d(node_depth, node_vp, k);
+}
+
+double orc_loglhood_voro(int k, const double *node_depth, const double *node_vp,
+                         const double *src_offset, const double *src_depth, int nsrc,
+                         const double *tobs, double sigma, double *tpred,
+                         double *sorted_depth, double *sorted_vp)
+{
+    double *d = (double *)malloc(sizeof(double) * (size_t)(2 * k + 2));
+    double *v = d + k + 1;
+    memcpy(d, node_depth, sizeof(double) * (size_t)k);
+    memcpy(v, node_vp, sizeof(double) * (size_t)k);
+    orc_interplayer_novar(k, d, v);
+    if (sorted_depth) memcpy(sorted_depth, d, sizeof(double) * (size_t)k);
+    if (sorted_vp) memcpy(sorted_vp, v, sizeof(double) * (size_t)k);
+    double ll = orc_loglhood_rt(k, v, d + 1, src_offset, src_depth, nsrc, tobs, sigma, tpred);
+    free(d);
+    return ll;
+}

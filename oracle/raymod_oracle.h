@@ -93,6 +93,16 @@ double orc_loglhood_rt(int k, const double *vp, const double *ziface,
                        const double *src_offset, const double *src_depth, int nsrc,
                        const double *tobs, double sigma, double *tpred);
 
+/* "Next" row N1: INTERPLAYER_novar (loglhood.f90:214-295) -- sort the k Voronoi nodes by depth
+ * with the reference's quicksort (quicksort.f90:66-123), in place. */
+void orc_interplayer_novar(int k, double *node_depth, double *node_vp);
+/* INTERPLAYER_novar followed by LOGLHOOD_RT on unsorted nodes; sorted_* (may be NULL) get the
+ * sorted nodes. */
+double orc_loglhood_voro(int k, const double *node_depth, const double *node_vp,
+                         const double *src_offset, const double *src_depth, int nsrc,
+                         const double *tobs, double sigma, double *tpred,
+                         double *sorted_depth, double *sorted_vp);
+
 /* Aggregate trace counters over a batch (for W_ref / W_min flop accounting). */
 typedef struct {
     long long rays, top, neg, safe, bisect;

@@ -52,7 +52,7 @@ struct Ctx {
     cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t  ev_h2d[kMaxChunks], ev_k0[kMaxChunks], ev_k1[kMaxChunks];
     cudaEvent_t  ev_t0 = nullptr, ev_t1 = nullptr;
-    DevBuf vels, depths, nl, off, dep, cosv, tobs, sigma, timeP, pout, logL, arena;
+    DevBuf vels, depths, nl, off, dep, cosv, tobs, sigma, timeP, pout, logL, arena, voro, vsorted;
     void  *pin = nullptr;          // pinned staging for small calls
     size_t pin_cap = 0;
     // options (<= 0: automatic)
@@ -520,6 +520,61 @@ int loglhood_batch(const int *k, const double *vp, const double *ziface, const i
     return run_host(h);
 }
 
+int loglhood_batch_voro(const int *k, const double *voro, const int *B, const int *ldk,
+                        const double *src_offset, const double *src_depth, const int *NSrc,
+                        const double *tobs, const double *sigma, double *logL, double *tpred,
+                        double *voro_sorted) {
+    if (int rc = ensure_init()) return rc;
+    g.err.clear();
+    g.kernel_ms = g.total_ms = 0.0;
+    const int nb = *B, ld = *ldk, ns = *NSrc;
+    if (nb <= 0 || ns <= 0) return 0;
+    if (ld < 1 || ld > 64) return fail("loglhood_batch_voro supports 1..64 nodes per state");
+    if (!logL || !tobs || !sigma) return fail("loglhood_batch_voro needs tobs, sigma and logL");
+    const size_t Bz = (size_t)nb, S = (size_t)ns;
+    TileCfg cfg;
+    if (int rc = choose_cfg(nb, ld, ld, ns, true, cfg)) return rc;
+    const size_t Bpad = (Bz + cfg.M - 1) / cfg.M * cfg.M + cfg.M;
+    CK(g.voro.reserve(Bz * 2 * ld * 8));
+    if (voro_sorted) CK(g.vsorted.reserve(Bz * 2 * ld * 8));
+    CK(g.vels.reserve(Bpad * ld * 8));
+    CK(g.depths.reserve(Bpad * ld * 8));
+    CK(g.nl.reserve(Bpad * 4));
+    CK(g.off.reserve(S * 8)); CK(g.dep.reserve(S * 8)); CK(g.cosv.reserve(S * 8)); CK(g.tobs.reserve(S * 8));
+    CK(g.sigma.reserve(Bz * 8)); CK(g.logL.reserve(Bz * 8));
+    if (tpred) CK(g.timeP.reserve(Bz * S * 8));
+    cudaStream_t st = g.s_comp;
+    CK(cudaMemcpyAsync(g.voro.p, voro, Bz * 2 * ld * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(g.nl.p, k, Bz * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(g.off.p, src_offset, S * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(g.dep.p, src_depth, S * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(g.tobs.p, tobs, S * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(g.sigma.p, sigma, Bz * 8, cudaMemcpyHostToDevice, st));
+    CK(rtb::launch_prep_sources(g.off.as<double>(), g.dep.as<double>(), g.cosv.as<double>(), ns, st));
+    CK(rtb::launch_prep_voro(g.nl.as<int>(), g.voro.as<double>(), nb, ld, g.vels.as<double>(),
+                             g.depths.as<double>(), voro_sorted ? g.vsorted.as<double>() : nullptr, st));
+    BatchArgs a{};
+    a.vels = g.vels.as<double>(); a.depths = g.depths.as<double>(); a.nlayers = g.nl.as<int>();
+    a.B = nb; a.ldv = ld; a.ldz = ld; a.kmode = 1;
+    a.src_offset = g.off.as<double>(); a.src_depth = g.dep.as<double>(); a.src_cos = g.cosv.as<double>();
+    a.tobs = g.tobs.as<double>(); a.nsrc = ns; a.sigma = g.sigma.as<double>();
+    a.timeP = tpred ? g.timeP.as<double>() : nullptr; a.p_out = nullptr; a.logL = g.logL.as<double>();
+    a.logc = log_norm_const(ns);
+    a.padded = 1;
+    CK(cudaEventRecord(g.ev_k0[0], st));
+    CK(rtb::launch_batch(a, cfg, st));
+    CK(cudaEventRecord(g.ev_k1[0], st));
+    g.launches += 3;
+    g.last = cfg;
+    CK(cudaMemcpyAsync(logL, g.logL.p, Bz * 8, cudaMemcpyDeviceToHost, st));
+    if (tpred) CK(cudaMemcpyAsync(tpred, g.timeP.p, Bz * S * 8, cudaMemcpyDeviceToHost, st));
+    if (voro_sorted) CK(cudaMemcpyAsync(voro_sorted, g.vsorted.p, Bz * 2 * ld * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g.ev_k0[0], g.ev_k1[0]) == cudaSuccess) g.kernel_ms = g.total_ms = ms;
+    return 0;
+}
+
 int rtb200_dff_batch_device(const double *d_vels, const double *d_depths, const int *d_nlayers,
                             int B, int ldv, int ldz, const double *d_src_offset,
                             const double *d_src_depth, int NSrc, double *d_timeP,
@@ -566,7 +621,7 @@ void rtb200_shutdown(void) {
     g.pin = nullptr;
     g.pin_cap = 0;
     for (DevBuf *b : {&g.vels, &g.depths, &g.nl, &g.off, &g.dep, &g.cosv, &g.tobs, &g.sigma,
-                      &g.timeP, &g.pout, &g.logL, &g.arena})
+                      &g.timeP, &g.pout, &g.logL, &g.arena, &g.voro, &g.vsorted})
         b->release();
     for (int i = 0; i < kMaxChunks; ++i) {
         cudaEventDestroy(g.ev_h2d[i]);

@@ -53,6 +53,8 @@ size_t      tile_smem_bytes(const TileCfg &c, int ldv, int ldz);
 cudaError_t launch_prep_sources(const double *off, const double *dep, double *cosv, int nsrc,
                                 cudaStream_t st);
 cudaError_t launch_batch(const BatchArgs &a, const TileCfg &c, cudaStream_t st);
+cudaError_t launch_prep_voro(const int *k, const double *voro, int B, int ldk, double *vels,
+                             double *depths, double *sorted, cudaStream_t st);
 int         max_ctas_per_sm(const TileCfg &c);   // occupancy of the batch kernel for this geometry
 cudaError_t fp64_peak(double *tflops, int repeats, cudaStream_t st);
 cudaError_t fastpath_selftest(double samples, unsigned long long seed, double *mismatches,

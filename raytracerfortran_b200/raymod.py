@@ -118,6 +118,28 @@ def loglhood_batch(k, voro_vp, ziface, src_offset, src_depth, DobsRT, sdparRT, w
     return ll, pred
 
 
+def loglhood_batch_voro(k, voro, src_offset, src_depth, DobsRT, sdparRT, want_pred=False,
+                        want_sorted=False):
+    """INTERPLAYER_novar + LOGLHOOD (loglhood.f90:214-295, :3-211) over B chain states given as
+    unsorted Voronoi nodes voro[B, 2, ldk] (depth row, vp row).  Returns (logL[B], DpredRT or
+    None, sorted voro or None)."""
+    vo = _d(voro)
+    kk = np.ascontiguousarray(k, dtype=np.int32)
+    so, sd, ob, sg = _d(src_offset), _d(src_depth), _d(DobsRT), _d(sdparRT)
+    if vo.ndim != 3 or vo.shape[1] != 2:
+        raise ValueError("voro must be [B, 2, ldk]")
+    B, ldk, nsrc = vo.shape[0], vo.shape[2], so.size
+    if B and (kk.min() < 1 or kk.max() > ldk):
+        raise ValueError("k out of range")
+    ll = np.empty(B)
+    pred = np.empty((B, nsrc)) if want_pred else None
+    srt = np.empty_like(vo) if want_sorted else None
+    rc = _lib.load().loglhood_batch_voro(kk.ctypes.data_as(_IP), _p(vo), _ci(B), _ci(ldk), _p(so),
+                                         _p(sd), _ci(nsrc), _p(ob), _p(sg), _p(ll), _p(pred), _p(srt))
+    _lib.check(rc)
+    return ll, pred, srt
+
+
 def set_option(name, value):
     if _lib.load().rtb200_set_option(name.encode(), float(value)) != 0:
         raise KeyError(name)

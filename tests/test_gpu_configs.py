@@ -83,3 +83,37 @@ def test_config5_stress_slice():
     assert np.array_equal(got["logL"][pick], ref["logL"])
     only_ll = rt.dff_batch(v, z, nl, so, sd, tobs=tobs, sigma=sigma, want_times=False)
     assert np.array_equal(only_ll["logL"], got["logL"])
+
+
+def test_next_row_n1_device_side_interplayer_novar():
+    """chain states arrive as UNSORTED Voronoi nodes; the device sorts
+    them with the reference's quicksort (ties included) and evaluates LOGLHOOD."""
+    rng = np.random.default_rng(17)
+    B, kmax, nsrc = 3000, 30, 64
+    k, vp, zi = workloads.make_transd_models(B, kmax, 8, uniform_k=True)
+    voro = np.zeros((B, 2, kmax))
+    for b in range(B):
+        kb = k[b]
+        dep = np.concatenate(([0.0], zi[b, :kb - 1]))
+        perm = rng.permutation(kb)
+        voro[b, 0, :kb] = dep[perm]
+        voro[b, 1, :kb] = vp[b, :kb][perm]
+    # ties in depth: the result depends on where the reference's Hoare partition leaves them
+    voro[:200, 0, 1] = voro[:200, 0, 0]
+    so, sd = workloads.make_sources(nsrc, 8)
+    tobs, sigma = workloads.make_observations(np.full(nsrc, 1.2), B, 8)
+    ll, pred, srt = rt.loglhood_batch_voro(k, voro, so, sd, tobs, sigma, want_pred=True, want_sorted=True)
+    for b in list(range(0, 260, 7)) + list(range(260, B, 41)):
+        kb = k[b]
+        w_ll, w_pred, w_d, w_v = oracle.loglhood_voro(voro[b, 0, :kb], voro[b, 1, :kb], so, sd, tobs, sigma[b])
+        assert np.array_equal(srt[b, 0, :kb], w_d) and np.array_equal(srt[b, 1, :kb], w_v)
+        assert np.array_equal(bits(pred[b]), bits(w_pred))
+        assert logl_close(np.array([ll[b]]), np.array([w_ll]), nsrc, sigma[b:b + 1])
+    # sorted input: identical to loglhood_batch on the prepared rows
+    ll2, _ = rt.loglhood_batch(k, vp, zi, so, sd, tobs, sigma)
+    same_rows = np.arange(200, B)
+    voro2 = np.zeros((B, 2, kmax))
+    voro2[:, 1, :] = vp
+    voro2[:, 0, 1:] = zi
+    ll3, _, _ = rt.loglhood_batch_voro(k, voro2, so, sd, tobs, sigma)
+    assert np.array_equal(bits(ll3[same_rows]), bits(ll2[same_rows]))

@@ -121,3 +121,19 @@ def test_rays_dat_writer_roundtrip(golden, tmp_path):
     # list-directed look: 3 blanks, 17 significant digits, 5 blanks
     first = open(path).readline()
     assert first.startswith("   2727.72106786829") and first.rstrip("\n").endswith("     ")
+
+
+def test_interplayer_novar_sort_matches_a_plain_sort_and_is_deterministic_on_ties():
+    """The oracle's restatement of QSORTC2D (quicksort.f90:66-123) used by INTERPLAYER_novar."""
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        k = int(rng.integers(1, 31))
+        dep, vp = rng.uniform(0, 9000, k), rng.uniform(1500, 9000, k)
+        _, _, sd_, sv_ = oracle.loglhood_voro(dep, vp, [100.0], [500.0], [0.3], 0.02)
+        order = np.argsort(dep, kind="stable")
+        assert np.array_equal(sd_, dep[order]) and np.array_equal(sv_, vp[order])
+    dep = np.array([0.0, 3000.0, 1000.0, 2000.0, 1000.0])
+    vp = np.array([3000.0, 6000.0, 4000.0, 5000.0, 4500.0])
+    _, _, sd_, sv_ = oracle.loglhood_voro(dep, vp, [100.0], [500.0], [0.3], 0.02)
+    assert sd_.tolist() == [0.0, 1000.0, 1000.0, 2000.0, 3000.0]
+    assert sorted(sv_[1:3].tolist()) == [4000.0, 4500.0]
