@@ -280,9 +280,10 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        traffic = None
+        traffic = ncu = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("dram_bytes_per_launch")
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = ncu.get("dram_bytes_per_launch")
         except Exception:
             pass
         line = {
@@ -312,6 +313,8 @@ def main():
                 "peak_source": "measured live: DFMA microbenchmark in libraytrace_b200 "
                                "(MEASURED_PEAKS.json has no FP64 entry)",
                 "flops_per_eval_min": w_min, "flops_per_eval_reference": w_ref,
+                "fp64_pipe_active_pct_ncu": (ncu or {}).get("fp64_pipe_active_pct"),
+                "ncu_source": (ncu or {}).get("source"),
                 "note": "sqrt = div = 1 flop; a correctly rounded fp64 div/sqrt costs ~10 FP64-pipe "
                         "instructions, so pipe utilisation (ncu, profiles/) is several times this fraction",
                 "hbm": {"achieved_GBps": alg_bytes / kernel_s / 1e9, "peak_GBps": peaks.get("hbm_gbs"),
