@@ -66,6 +66,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.sm, self.reasons, self.sm_max = index, False, [], set(), None
+        self.recording = False      # NVML is initialised before the timed region; samples count only inside it
 
     def run(self):
         try:
@@ -81,6 +82,9 @@ class ClockSampler(threading.Thread):
                 getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
             }
             while not self.stop_flag:
+                if not self.recording:
+                    time.sleep(0.001)
+                    continue
                 self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -89,7 +93,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.02)
+                time.sleep(0.005)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -211,11 +215,12 @@ def main():
         torch.cuda.synchronize()
 
     peak_tf = rt.fp64_peak_tflops(3)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step_resident()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.recording = True
     launches0 = rt.get_stat("launches")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
