@@ -88,6 +88,18 @@ int loglhood_batch(const int *k, const double *vp, const double *ziface,
                    const double *tobs, const double *sigma,
                    double *logL, double *tpred);
 
+/* loglhood_batch with the AR(1) residual error model of IAR = 1 (loglhood.f90:171-182;
+ * ARPRED_RT :616-653, CHECKBOUNDS_ARMXRT :678-699; off in every shipped parameter file):
+ * for states with idxar[b] == 1, DarRT(i) = arpar[b] * DresRT(i-1) for 1 < i < NSrc and 0 at both
+ * ends, the residual becomes DresRT - DarRT, and a state whose |DarRT| exceeds *armx (the
+ * reference's armxRT = 0.5, rjmcmc_com.f90:93) gets logL = -HUGE.  idxar == NULL is loglhood_batch. */
+int loglhood_batch_ar(const int *k, const double *vp, const double *ziface,
+                      const int *B, const int *ldv, const int *ldz,
+                      const double *src_offset, const double *src_depth, const int *NSrc,
+                      const double *tobs, const double *sigma,
+                      const int *idxar, const double *arpar, const double *armx,
+                      double *logL, double *tpred);
+
 /* INTERPLAYER_novar + LOGLHOOD (loglhood.f90:214-295 then :3-211) over B chain states given as
  * UNSORTED Voronoi nodes: voro[b][0][i] = depth, voro[b][1][i] = vp of node i (Fortran
  * voro(ldk, 2, B)), k[b] <= ldk <= 64 nodes.  The nodes are sorted by depth on the device with

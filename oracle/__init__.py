@@ -68,6 +68,8 @@ def lib():
                                                 C.c_int, dp, C.c_char_p]
         _lib.orc_loglhood_voro.restype = C.c_double
         _lib.orc_loglhood_voro.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, dp, C.c_double, dp, dp, dp]
+        _lib.orc_loglhood_from_times_ar.restype = C.c_double
+        _lib.orc_loglhood_from_times_ar.argtypes = [dp, dp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]
         _lib.orc_batch_stats.restype = None
         _lib.orc_batch_stats.argtypes = [dp, dp, ip, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int,
                                          C.POINTER(Stats)]
@@ -102,6 +104,11 @@ def trace_rays(vels, depths, src_offset, src_depth, keep_delta=-1, rays_path=Non
 def loglhood_from_times(tpred, tobs, sigma):
     a, b = _d(tpred), _d(tobs)
     return lib().orc_loglhood_from_times(_p(a), _p(b), a.size, float(sigma))
+
+
+def loglhood_from_times_ar(tpred, tobs, sigma, idxar, arpar, armx=0.5):
+    a, b = _d(tpred), _d(tobs)
+    return lib().orc_loglhood_from_times_ar(_p(a), _p(b), a.size, float(sigma), int(idxar), float(arpar), float(armx))
 
 
 def loglhood_rt(vp, ziface, src_offset, src_depth, tobs, sigma):

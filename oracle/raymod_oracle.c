@@ -500,3 +500,31 @@ double orc_loglhood_voro(int k, const double *node_depth, const double *node_vp,
     free(d);
     return ll;
 }
+
+/* ---- "next" row N4: the AR(1) residual error model of IAR = 1 ------------------------ *
+ * ll:171-182: DarRT from ARPRED_RT (ll:616-653, order 1: DarRT(i) = arpar*DresRT(i-1) for
+ * 1 < i < N, 0 at both ends), DresRT = DresRT - DarRT, CHECKBOUNDS_ARMXRT (ll:678-699) rejects
+ * the state (logL = -HUGE) when MAXVAL(DarRT) > armx or MINVAL(DarRT) < -armx.            */
+double orc_loglhood_from_times_ar(const double *tpred, const double *tobs, int ndat, double sigma,
+                                  int idxar, double arpar, double armx)
+{
+    double *res = (double *)malloc(sizeof(double) * (size_t)(ndat > 0 ? ndat : 1));
+    double *dar = (double *)calloc((size_t)(ndat > 0 ? ndat : 1), sizeof(double));
+    for (int i = 0; i < ndat; ++i) res[i] = tobs[i] - tpred[i];            /* ll:166 */
+    if (idxar == 1) {
+        for (int i = 1; i < ndat; ++i) dar[i] = 0.0 + arpar * res[i - 1];  /* ll:640-650, k = 1 */
+        if (ndat > 0) { dar[0] = 0.0; dar[ndat - 1] = 0.0; }               /* ll:652-653 */
+    }
+    int bad = 0;
+    double mx = -DBL_MAX, mn = DBL_MAX;
+    for (int i = 0; i < ndat; ++i) { if (dar[i] > mx) mx = dar[i]; if (dar[i] < mn) mn = dar[i]; }
+    if (ndat > 0 && (mx > armx || mn < -armx)) bad = 1;                    /* ll:686-695 */
+    double ss = 0.0;
+    for (int i = 0; i < ndat; ++i) { double r = res[i] - dar[i]; ss = ss + r * r; }   /* ll:178,195 */
+    double n = (double)ndat;
+    double logL = log(1.0 / pow(2.0 * ORC_PI, n / 2.0)) - (ss / (2.0 * (sigma * sigma)) + n * log(sigma));
+    if (isnan(logL)) logL = -DBL_MAX;
+    if (bad) logL = -DBL_MAX;                                              /* ll:204-206 */
+    free(res); free(dar);
+    return logL;
+}

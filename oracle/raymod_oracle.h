@@ -103,6 +103,11 @@ double orc_loglhood_voro(int k, const double *node_depth, const double *node_vp,
                          const double *tobs, double sigma, double *tpred,
                          double *sorted_depth, double *sorted_vp);
 
+/* "Next" row N4: LOGLHOOD_RT's likelihood with the AR(1) residual model of IAR = 1
+ * (loglhood.f90:171-182, ARPRED_RT :616-653, CHECKBOUNDS_ARMXRT :678-699). */
+double orc_loglhood_from_times_ar(const double *tpred, const double *tobs, int ndat, double sigma,
+                                  int idxar, double arpar, double armx);
+
 /* Aggregate trace counters over a batch (for W_ref / W_min flop accounting). */
 typedef struct {
     long long rays, top, neg, safe, bisect;

@@ -11,7 +11,7 @@ AntonBiryukovUofC/RayTracerFortran.
 """
 from ._lib import EXPORTS, LIB_PATH, RayTraceError  # noqa: F401
 from .raymod import (TraceRays, dff, dff7, dff_batch, fp64_peak_tflops, get_stat,  # noqa: F401
-                     loglhood_batch, loglhood_batch_voro, selftest_fast_division, set_option, shard_range)
+                     loglhood_batch, loglhood_batch_ar, loglhood_batch_voro, selftest_fast_division, set_option, shard_range)
 
-__all__ = ["dff", "dff7", "TraceRays", "dff_batch", "loglhood_batch", "loglhood_batch_voro", "set_option", "get_stat",
+__all__ = ["dff", "dff7", "TraceRays", "dff_batch", "loglhood_batch", "loglhood_batch_ar", "loglhood_batch_voro", "set_option", "get_stat",
            "fp64_peak_tflops", "shard_range", "selftest_fast_division", "RayTraceError", "EXPORTS", "LIB_PATH"]

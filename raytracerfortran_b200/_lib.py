@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "libraytrace_b200
 
 # every symbol include/raytrace_b200.h declares
 EXPORTS = (
-    "dff_", "dff7_", "tracerays_", "dff_batch", "loglhood_batch", "loglhood_batch_voro",
+    "dff_", "dff7_", "tracerays_", "dff_batch", "loglhood_batch", "loglhood_batch_ar", "loglhood_batch_voro",
     "rtb200_dff_batch_device",
     "rtb200_init", "rtb200_shutdown", "rtb200_last_error", "rtb200_device_count",
     "rtb200_set_option", "rtb200_get_stat", "rtb200_fp64_peak_tflops", "rtb200_shard_range",
@@ -47,6 +47,8 @@ def load():
     lib.dff_batch.argtypes = [dp, dp, ip, ip, ip, ip, dp, dp, ip, dp, dp, dp, dp, dp]
     lib.loglhood_batch.restype = i
     lib.loglhood_batch.argtypes = [ip, dp, dp, ip, ip, ip, dp, dp, ip, dp, dp, dp, dp]
+    lib.loglhood_batch_ar.restype = i
+    lib.loglhood_batch_ar.argtypes = [ip, dp, dp, ip, ip, ip, dp, dp, ip, dp, dp, ip, dp, dp, dp, dp]
     lib.loglhood_batch_voro.restype = i
     lib.loglhood_batch_voro.argtypes = [ip, dp, ip, ip, dp, dp, ip, dp, dp, dp, dp, dp]
     lib.rtb200_dff_batch_device.restype = i

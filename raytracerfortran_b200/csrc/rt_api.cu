@@ -52,7 +52,8 @@ struct Ctx {
     cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t  ev_h2d[kMaxChunks], ev_k0[kMaxChunks], ev_k1[kMaxChunks];
     cudaEvent_t  ev_t0 = nullptr, ev_t1 = nullptr;
-    DevBuf vels, depths, nl, off, dep, cosv, tobs, sigma, timeP, pout, logL, arena, voro, vsorted;
+    DevBuf vels, depths, nl, off, dep, cosv, tobs, sigma, timeP, pout, logL, arena, voro, vsorted,
+        idxar, arparb;
     void  *pin = nullptr;          // pinned staging for small calls
     size_t pin_cap = 0;
     // options (<= 0: automatic)
@@ -194,6 +195,9 @@ struct HostCall {
     double *timeP;
     const double *tobs, *sigma;
     double *logL, *p_out;
+    const int    *idxar = nullptr;     // AR(1) residual model: per-state switch, coefficient, bound
+    const double *arpar = nullptr;
+    double        armx  = 0.0;
 };
 
 // Small calls (the one-model dff_ of R's .Fortran, a handful of proposals): everything goes
@@ -286,7 +290,7 @@ int run_host(const HostCall &h) {
     {
         const size_t io = (B * (h.ldv + ldz + 2) + 3 * S) * 8 +
                           ((h.timeP ? B * S : 0) + (h.p_out ? B * S : 0) + (h.logL ? B : 0)) * 8;
-        if (io <= kSmallBytes) return run_host_small(h, cfg, ldz);
+        if (io <= kSmallBytes && !h.idxar) return run_host_small(h, cfg, ldz);
     }
     // our own buffers are padded to whole tiles, so TMA is always legal on them
     const size_t Bpad = (B + cfg.M - 1) / cfg.M * cfg.M + cfg.M;
@@ -301,6 +305,10 @@ int run_host(const HostCall &h) {
     if (h.timeP) CK(g.timeP.reserve(B * S * 8));
     if (h.p_out) CK(g.pout.reserve(B * S * 8));
     if (h.logL) CK(g.logL.reserve(B * 8));
+    if (h.idxar) {
+        CK(g.idxar.reserve(B * 4));
+        CK(g.arparb.reserve(B * 8));
+    }
 
     CK(cudaEventRecord(g.ev_t0, g.s_h2d));
     CK(cudaMemcpyAsync(g.off.p, h.off, S * 8, cudaMemcpyHostToDevice, g.s_h2d));
@@ -329,6 +337,12 @@ int run_host(const HostCall &h) {
         if (h.sigma)
             CK(cudaMemcpyAsync(g.sigma.as<double>() + j0, h.sigma + j0, nb * 8,
                                cudaMemcpyHostToDevice, g.s_h2d));
+        if (h.idxar) {
+            CK(cudaMemcpyAsync(g.idxar.as<int>() + j0, h.idxar + j0, nb * 4, cudaMemcpyHostToDevice,
+                               g.s_h2d));
+            CK(cudaMemcpyAsync(g.arparb.as<double>() + j0, h.arpar + j0, nb * 8,
+                               cudaMemcpyHostToDevice, g.s_h2d));
+        }
         CK(cudaEventRecord(g.ev_h2d[j], g.s_h2d));
 
         BatchArgs a{};
@@ -345,6 +359,9 @@ int run_host(const HostCall &h) {
         a.logL = h.logL ? g.logL.as<double>() + j0 : nullptr;
         a.logc = logc;
         a.padded = 1;
+        a.idxar = h.idxar ? g.idxar.as<int>() + j0 : nullptr;
+        a.arpar = h.idxar ? g.arparb.as<double>() + j0 : nullptr;
+        a.armx = h.armx;
         TileCfg cj = cfg;
         const int ntiles = (int)((nb + cfg.M - 1) / cfg.M);
         cj.grid = std::max(1, std::min(ntiles, g.sms * g.last_ctas));
@@ -520,6 +537,21 @@ int loglhood_batch(const int *k, const double *vp, const double *ziface, const i
     return run_host(h);
 }
 
+int loglhood_batch_ar(const int *k, const double *vp, const double *ziface, const int *B,
+                      const int *ldv, const int *ldz, const double *src_offset,
+                      const double *src_depth, const int *NSrc, const double *tobs,
+                      const double *sigma, const int *idxar, const double *arpar,
+                      const double *armx, double *logL, double *tpred) {
+    HostCall h{};
+    h.vels = vp; h.depths = ziface; h.nlayers = k;
+    h.B = *B; h.ldv = *ldv; h.ldz = *ldz; h.kmode = 1;
+    h.off = src_offset; h.dep = src_depth; h.nsrc = *NSrc;
+    h.timeP = tpred; h.tobs = tobs; h.sigma = sigma; h.logL = logL; h.p_out = nullptr;
+    h.idxar = idxar; h.arpar = arpar; h.armx = armx ? *armx : 0.5;
+    if (idxar && !arpar) return fail("loglhood_batch_ar needs arpar with idxar");
+    return run_host(h);
+}
+
 int loglhood_batch_voro(const int *k, const double *voro, const int *B, const int *ldk,
                         const double *src_offset, const double *src_depth, const int *NSrc,
                         const double *tobs, const double *sigma, double *logL, double *tpred,
@@ -621,7 +653,7 @@ void rtb200_shutdown(void) {
     g.pin = nullptr;
     g.pin_cap = 0;
     for (DevBuf *b : {&g.vels, &g.depths, &g.nl, &g.off, &g.dep, &g.cosv, &g.tobs, &g.sigma,
-                      &g.timeP, &g.pout, &g.logL, &g.arena, &g.voro, &g.vsorted})
+                      &g.timeP, &g.pout, &g.logL, &g.arena, &g.voro, &g.vsorted, &g.idxar, &g.arparb})
         b->release();
     for (int i = 0; i < kMaxChunks; ++i) {
         cudaEventDestroy(g.ev_h2d[i]);

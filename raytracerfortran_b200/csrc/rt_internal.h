@@ -34,6 +34,10 @@ struct BatchArgs {
     double       *logL;        // [B] or null
     double        logc;        // log(1/(2 pi)^(N/2)), computed once on the host
     int           padded;      // vels/depths are readable up to a whole number of tiles
+    // AR(1) residual model (IAR = 1: ARPRED_RT + CHECKBOUNDS_ARMXRT, loglhood.f90:171-182,616-701)
+    const int    *idxar;       // [B] or null: obj%idxarRT(1), 1 = apply the AR model to this state
+    const double *arpar;       // [B] obj%arparRT(1)
+    double        armx;        // armxRT: |DarRT| beyond it rejects the state (logL = -HUGE)
 };
 
 // Tile geometry chosen by the host for one launch.

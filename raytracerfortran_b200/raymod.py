@@ -118,6 +118,29 @@ def loglhood_batch(k, voro_vp, ziface, src_offset, src_depth, DobsRT, sdparRT, w
     return ll, pred
 
 
+def loglhood_batch_ar(k, voro_vp, ziface, src_offset, src_depth, DobsRT, sdparRT, idxarRT, arparRT,
+                      armxRT=0.5, want_pred=False):
+    """loglhood_batch with the AR(1) residual error model (IAR = 1; loglhood.f90:171-182,616-701):
+    idxarRT[B] switches it per state, arparRT[B] is the coefficient, armxRT the bound."""
+    v, z = _d(voro_vp), _d(ziface)
+    kk = np.ascontiguousarray(k, dtype=np.int32)
+    ix = np.ascontiguousarray(idxarRT, dtype=np.int32)
+    so, sd, ob, sg, ap = _d(src_offset), _d(src_depth), _d(DobsRT), _d(sdparRT), _d(arparRT)
+    B, nsrc = v.shape[0], so.size
+    if z.ndim != 2:
+        z = z.reshape(B, -1)
+    if ix.size != B or ap.size != B:
+        raise ValueError("idxarRT and arparRT must be [B]")
+    ll = np.empty(B)
+    pred = np.empty((B, nsrc)) if want_pred else None
+    rc = _lib.load().loglhood_batch_ar(kk.ctypes.data_as(_IP), _p(v), _p(z) if z.size else None,
+                                       _ci(B), _ci(v.shape[1]), _ci(z.shape[1]), _p(so), _p(sd),
+                                       _ci(nsrc), _p(ob), _p(sg), ix.ctypes.data_as(_IP), _p(ap),
+                                       C.byref(C.c_double(float(armxRT))), _p(ll), _p(pred))
+    _lib.check(rc)
+    return ll, pred
+
+
 def loglhood_batch_voro(k, voro, src_offset, src_depth, DobsRT, sdparRT, want_pred=False,
                         want_sorted=False):
     """INTERPLAYER_novar + LOGLHOOD (loglhood.f90:214-295, :3-211) over B chain states given as

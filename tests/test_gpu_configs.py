@@ -117,3 +117,31 @@ def test_next_row_n1_device_side_interplayer_novar():
     voro2[:, 0, 1:] = zi
     ll3, _, _ = rt.loglhood_batch_voro(k, voro2, so, sd, tobs, sigma)
     assert np.array_equal(bits(ll3[same_rows]), bits(ll2[same_rows]))
+
+
+def test_next_row_n4_ar1_residual_model():
+    """IAR = 1 -- ARPRED_RT (order 1) + CHECKBOUNDS_ARMXRT fused into the
+    likelihood (loglhood.f90:171-182,616-701), incl. states rejected by the |DarRT| bound, states
+    with the AR model switched off, and sources spilling over several chunks."""
+    rng = np.random.default_rng(23)
+    for B, nsrc in ((700, 64), (90, 300)):
+        k, vp, zi = workloads.make_transd_models(B, 12, 9, uniform_k=True)
+        so, sd = workloads.make_sources(nsrc, 9)
+        t0 = oracle.loglhood_rt(vp[3, :k[3]], zi[3, :max(k[3] - 1, 0)], so, sd, np.zeros(nsrc), 1.0)[1]
+        tobs, sigma = workloads.make_observations(t0, B, 9)
+        idx = (rng.random(B) < 0.7).astype(np.int32)
+        ar = rng.uniform(-0.9, 0.9, B)
+        ar[:40] = rng.uniform(3.0, 30.0, 40)            # large coefficients: |DarRT| > armx for most
+        ll, pred = rt.loglhood_batch_ar(k, vp, zi, so, sd, tobs, sigma, idx, ar, armxRT=0.5, want_pred=True)
+        plain, _ = rt.loglhood_batch(k, vp, zi, so, sd, tobs, sigma)
+        rejected = 0
+        for b in range(B):
+            want = oracle.loglhood_from_times_ar(pred[b], tobs, sigma[b], idx[b], ar[b], 0.5)
+            if want == -np.finfo(float).max:
+                rejected += 1
+                assert ll[b] == want
+            else:
+                assert logl_close(np.array([ll[b]]), np.array([want]), nsrc, sigma[b:b + 1])
+            if idx[b] == 0:
+                assert ll[b] == plain[b]
+        assert rejected > 0
