@@ -131,7 +131,9 @@ void        rtb200_shutdown(void);
 const char *rtb200_last_error(void);          /* "" when the last call succeeded               */
 int         rtb200_device_count(void);        /* 0 without a driver / device                   */
 /* options: "variant" (0 lock-step loops, 1 lane state machine), "threads", "tile_models",
- *          "tile_sources", "chunk_models", "ctas_per_sm"; <= 0 restores the default */
+ *          "tile_sources", "chunk_models", "ctas_per_sm"; <= 0 restores the default;
+ *          "logl_shuffle" (1: reduce the residuals of a model with a warp-shuffle tree instead of
+ *          the reference's source order -- same terms, ~N ulp from the ordered sum; default 0) */
 int         rtb200_set_option(const char *name, double value);
 /* stats of the last batched call: "kernel_ms", "total_ms", "launches" (cumulative),
  *          "tile_models", "tile_sources", "smem_bytes", "grid", "threads", "ctas_per_sm" */

@@ -58,7 +58,7 @@ struct Ctx {
     size_t pin_cap = 0;
     // options (<= 0: automatic)
     int opt_variant = 1, opt_threads = 0, opt_tile_models = 0, opt_tile_sources = 0,
-        opt_chunk_models = 0, opt_ctas = 0;
+        opt_chunk_models = 0, opt_ctas = 0, opt_logl_shuffle = 0;
     // stats
     double    kernel_ms = 0.0, total_ms = 0.0;
     long long launches = 0;
@@ -143,6 +143,7 @@ int choose_cfg(int B, int ldv, int ldz, int nsrc, bool aligned, TileCfg &c) {
     c.SC = std::min(nsrc, g.opt_tile_sources > 0 ? g.opt_tile_sources : 256);
     c.TS = c.SC | 1;
     c.use_tma = aligned ? 1 : 0;
+    c.logl_shuffle = g.opt_logl_shuffle;
     const int rays_target = c.threads * 8;
     int M = g.opt_tile_models > 0 ? g.opt_tile_models : std::max(2, rays_target / c.SC);
     M = even_up(std::min(M, even_up(B)));
@@ -684,6 +685,7 @@ int rtb200_set_option(const char *name, double value) {
     else if (!strcmp(name, "tile_sources")) g.opt_tile_sources = v;
     else if (!strcmp(name, "chunk_models")) g.opt_chunk_models = v;
     else if (!strcmp(name, "ctas_per_sm")) g.opt_ctas = v;
+    else if (!strcmp(name, "logl_shuffle")) g.opt_logl_shuffle = v > 0 ? 1 : 0;
     else return -1;
     return 0;
 }

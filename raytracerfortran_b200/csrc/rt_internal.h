@@ -50,6 +50,7 @@ struct TileCfg {
     int grid;     // persistent CTAs
     int variant;  // 0: lock-step loops, 1: lane state machine with refill
     int use_tma;  // rows are 16-byte aligned: stage with cp.async.bulk
+    int logl_shuffle;  // reduce the residuals with warp shuffles (tree order) instead of source order
     size_t smem;  // dynamic shared memory bytes
 };
 

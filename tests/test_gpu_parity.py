@@ -266,3 +266,21 @@ def test_config2_full_size_properties():
     assert np.all(T[conv] >= vertical[conv] * (1 - 1e-12))
     assert np.all(P > 0) and np.all(P < 1.0 / 1500.0)
     assert np.all(np.isfinite(LL))
+
+
+def test_warp_shuffle_likelihood_reduction_option():
+    """`logl_shuffle`: the residuals of a model are reduced by a warp-shuffle tree instead of in
+    source order; same terms, so logL stays within 1e-12 relative (north star: 1e-9)."""
+    B, nsrc = 900, 300
+    v, z, nl = workloads.make_models(B, 10, 41)
+    so, sd = workloads.make_sources(nsrc, 41)
+    ref = oracle.dff_batch(v, z, nl, so, sd)
+    tobs, sigma = workloads.make_observations(ref["timeP"][0], B, 41)
+    ref = oracle.dff_batch(v, z, nl, so, sd, tobs=tobs, sigma=sigma)
+    rt.set_option("logl_shuffle", 1)
+    try:
+        got = rt.dff_batch(v, z, nl, so, sd, tobs=tobs, sigma=sigma)
+    finally:
+        rt.set_option("logl_shuffle", 0)
+    assert_bitexact(got["timeP"], ref["timeP"], "timeP")
+    assert_logl_close(got["logL"], ref["logL"], nsrc, sigma)

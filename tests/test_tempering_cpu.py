@@ -35,11 +35,13 @@ def test_swap_rule_matches_tempswp_mh():
             assert bool(a) == want
         new = tempering.apply_swaps(beta, pairs, acc)
         assert sorted(new.tolist()) == sorted(beta.tolist())           # betas are permuted, never lost
-    # a colder chain always takes the better state: beta_j > beta_i and logL_i > logL_j => accept
-    p, a = tempering.swap_decisions([0.0, -1000.0], [0.1, 1.0], 1, 0)
-    i, j = p[0]
-    assert bool(a[0]) == ((np.array([0.1, 1.0])[j] - np.array([0.1, 1.0])[i])
-                          * (np.array([0.0, -1000.0])[i] - np.array([0.0, -1000.0])[j]) >= 0 or not a[0])
+    # the hot chain (beta 0.1) holds the much better state: the swap that hands it to the cold
+    # chain (beta 1.0) has logratio = +900 and is always accepted, whatever the pairing order
+    _, a = tempering.swap_decisions([0.0, -1000.0], [0.1, 1.0], 1, 0)
+    assert bool(a[0])
+    # the reverse (cold chain already holds the better state): logratio = -900, never accepted
+    _, a = tempering.swap_decisions([0.0, -1000.0], [1.0, 0.1], 1, 0)
+    assert not bool(a[0])
 
 
 def test_temperature_ladder():
