@@ -145,3 +145,31 @@ def test_next_row_n4_ar1_residual_model():
             if idx[b] == 0:
                 assert ll[b] == plain[b]
         assert rejected > 0
+
+
+def test_next_row_n3_replica_sweep_over_a_sample_file(tmp_path):
+    """parse a `_voro_sample.txt`, rebuild every kept state and
+    re-evaluate LOGLHOOD in one batched call (replica.f90:173-232)."""
+    from raytracerfortran_b200 import samplefile
+    B, nlmx, nsrc = 500, 10, 20
+    k, vp, zi = workloads.make_transd_models(B, nlmx, 14, uniform_k=True)
+    rng = np.random.default_rng(14)
+    voro = np.zeros((B, 2, nlmx))
+    for b in range(B):                                   # nodes in the sampler's arbitrary order
+        perm = rng.permutation(k[b])
+        voro[b, 0, :k[b]] = np.concatenate(([0.0], zi[b, :k[b] - 1]))[perm]
+        voro[b, 1, :k[b]] = vp[b, :k[b]][perm]
+    so, sd = workloads.make_sources(nsrc, 14)
+    sig = rng.uniform(0.001, 0.07, B)
+    rows = samplefile.pack_rows(np.zeros(B), np.zeros(B), np.zeros(B), k, voro, sig)
+    path = tmp_path / "t_voro_sample.txt"
+    samplefile.write_samples(path, rows)
+    tobs = 1.0 + 0.3 * rng.random(nsrc)
+    smp, ll, pred = samplefile.replica_sweep(path, nlmx, so, sd, tobs, burnin=50, thin=2)
+    assert len(ll) == len(range(50, B, 2))
+    for j in range(0, len(ll), 9):                       # oracle on the file's (9-digit) states
+        kb = smp["k"][j]
+        w_ll, w_pred, _, _ = oracle.loglhood_voro(smp["voro"][j, 0, :kb], smp["voro"][j, 1, :kb], so, sd,
+                                                  tobs, smp["sdparRT"][j, 0])
+        assert np.array_equal(bits(pred[j]), bits(w_pred))
+        assert logl_close(np.array([ll[j]]), np.array([w_ll]), nsrc, smp["sdparRT"][j])
