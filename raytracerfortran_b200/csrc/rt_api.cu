@@ -24,6 +24,7 @@ using rtb::TileCfg;
 
 constexpr double kPi = 3.141592653589793238462643383279502884197;  // data_type.f90:5 (PI2)
 constexpr int    kMaxChunks = 64;
+constexpr int    kDeepLdv = 40;     // models with this many velocities or more use the deep-model kernel
 
 struct DevBuf {
     void  *p = nullptr;
@@ -57,7 +58,7 @@ struct Ctx {
     void  *pin = nullptr;          // pinned staging for small calls
     size_t pin_cap = 0;
     // options (<= 0: automatic)
-    int opt_variant = 1, opt_threads = 0, opt_tile_models = 0, opt_tile_sources = 0,
+    int opt_variant = -1, opt_threads = 0, opt_tile_models = 0, opt_tile_sources = 0,
         opt_chunk_models = 0, opt_ctas = 0, opt_logl_shuffle = 0;
     // stats
     double    kernel_ms = 0.0, total_ms = 0.0;
@@ -137,7 +138,9 @@ int even_up(int x) { return (x + 1) & ~1; }
 // Tile geometry for one launch (DESIGN.md "tiling").
 int choose_cfg(int B, int ldv, int ldz, int nsrc, bool aligned, TileCfg &c) {
     if (ldv > 255) return fail("more than 254 interfaces per model are not supported");
-    c.variant = g.opt_variant ? 1 : 0;
+    // variant: 0 plain loops; 1 lane state machine; 3 the same with branch-free, two-step-unrolled
+    // layer loops for deep models (more registers, 2 CTAs/SM); default: by depth
+    c.variant = g.opt_variant < 0 ? (ldv >= kDeepLdv ? 3 : 1) : (g.opt_variant == 3 ? 3 : (g.opt_variant ? 1 : 0));
     c.threads = g.opt_threads > 0 ? std::min(256, (g.opt_threads + 31) / 32 * 32) : 256;
     c.LP = std::max(ldv, 2) | 1;
     c.SC = std::min(nsrc, g.opt_tile_sources > 0 ? g.opt_tile_sources : 256);
@@ -147,7 +150,7 @@ int choose_cfg(int B, int ldv, int ldz, int nsrc, bool aligned, TileCfg &c) {
     const int rays_target = c.threads * 8;
     int M = g.opt_tile_models > 0 ? g.opt_tile_models : std::max(2, rays_target / c.SC);
     M = even_up(std::min(M, even_up(B)));
-    const int want_ctas = g.opt_ctas > 0 ? g.opt_ctas : 3;
+    const int want_ctas = g.opt_ctas > 0 ? g.opt_ctas : (c.variant == 3 ? 2 : 3);
     const size_t budget  = (size_t)g.smem_optin;
     const size_t per_cta = std::min<size_t>(budget, (size_t)(227 * 1024) / want_ctas - 1024);
     for (;;) {
@@ -679,7 +682,7 @@ int rtb200_device_count(void) {
 
 int rtb200_set_option(const char *name, double value) {
     const int v = (int)value;
-    if (!strcmp(name, "variant")) g.opt_variant = v < 0 ? 1 : v;
+    if (!strcmp(name, "variant")) g.opt_variant = v < 0 ? -1 : v;
     else if (!strcmp(name, "threads")) g.opt_threads = v;
     else if (!strcmp(name, "tile_models")) g.opt_tile_models = v > 0 ? even_up(v) : 0;
     else if (!strcmp(name, "tile_sources")) g.opt_tile_sources = v;

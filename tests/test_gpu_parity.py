@@ -41,7 +41,7 @@ def assert_logl_close(got, want, nsrc, sigma):
 @pytest.fixture(autouse=True)
 def _defaults():
     for name in ("variant", "threads", "tile_models", "tile_sources", "chunk_models", "ctas_per_sm"):
-        rt.set_option(name, 1 if name == "variant" else 0)
+        rt.set_option(name, -1 if name == "variant" else 0)
     yield
 
 
@@ -92,7 +92,7 @@ def test_readme_example(golden):
 # ---------------------------------------------------------------------------------------------
 # batched sweeps against the oracle, both kernel variants
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 3])
 @pytest.mark.parametrize("B,nlayers,nsrc,seed", [(1500, 10, 64, 2), (257, 4, 20, 11), (64, 29, 256, 3),
                                                  (33, 1, 7, 5)])
 def test_dff_batch_bitexact(variant, B, nlayers, nsrc, seed):
@@ -109,7 +109,7 @@ def test_dff_batch_bitexact(variant, B, nlayers, nsrc, seed):
     assert rt.get_stat("variant") == variant
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 3])
 def test_near_critical_50_layers(variant):
     """config-5 style rays: p*v -> 1, ~99 % bisection, Newton clamps."""
     rt.set_option("variant", variant)
@@ -177,7 +177,7 @@ def test_edge_geometry():
     assert [oracle.which_layer(z[0], d) for d in sd[:5]] == [1, 2, 3, 3, 4]
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 3])
 def test_ragged_batches_and_chunking(variant):
     rt.set_option("variant", variant)
     rng = np.random.default_rng(77)
