@@ -21,8 +21,7 @@ marks = [("kernel prologue", kstart), ("A stage+tables", find("// --------------
 helpers = [("fp64 prims (dmul..dsqrt builtins)", find("double dmul(double a"), find("double dsqrt(double a") + 1),
            ("eval_time/eval_ffp (builtin path)", find("struct Tables"), find("// rsqrt-seeded square root")),
            ("sqrt_rsqrt", find("double sqrt_rsqrt("), find("double div_seeded(")),
-           ("div_seeded", find("double div_seeded("), find("// one layer's contribution")),
-           ("layer_ffp", find("// one layer's contribution"), find("// a / b by exactly")),
+           ("div_seeded", find("double div_seeded("), find("// a / b by exactly")),
            ("div_unchecked", find("// a / b by exactly"), find("// 32-bit shared-memory addressing")),
            ("lds/sts helpers", find("// 32-bit shared-memory addressing"), find("// Two consecutive layers")),
            ("layer_pair_ffp", find("// Two consecutive layers"), find("// variant 0: the solver"))]
