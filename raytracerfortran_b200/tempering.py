@@ -108,3 +108,22 @@ def evaluate_replicas(k, voro_vp, ziface, src_offset, src_depth, tobs, sigma, lo
                                   sigma=sigma.reshape(R * P),
                                   logL=None if logL is None else logL.reshape(R * P), kmode=True)
     return out["logL"].reshape(R, P)
+
+
+def mh_accept(logL_cur, logL_new, beta, u, logPr_new=None, outside=None):
+    """The Metropolis-Hastings decision of EXPLORE_MH_NOVARPAR (prjmh_temper_rf.f90:739-751) for a
+    batch of independent chains, one proposal each:
+
+        logPLratio = logPr_new + (logL_new - logL_cur) * beta;   reject iff u >= exp(logPLratio)
+
+    and proposals that left the prior bounds (CHECKBOUNDS2, `ioutside`) are rejected outright
+    (:753-757).  Tensors of any matching shape on any device; returns a bool tensor (True =
+    accept).  This is the rule only -- the reference's sampler applies it one proposal at a time
+    per chain; batching proposals across chains keeps each chain's kernel unchanged."""
+    ratio = (logL_new - logL_cur) * beta
+    if logPr_new is not None:
+        ratio = logPr_new + ratio
+    accept = ~(u >= torch.exp(ratio))
+    if outside is not None:
+        accept = accept & ~outside.to(torch.bool)
+    return accept

@@ -90,3 +90,21 @@ def test_swap_round_world_size_2_gloo():
         assert np.array_equal(h0[rnd][2], pairs) and np.array_equal(h1[rnd][2], pairs)
         assert np.array_equal(np.concatenate([h0[rnd][0], h1[rnd][0]]), beta_all)      # same ladder
     assert sum(int(h0[r][1].sum()) for r in range(5)) > 0                              # something swapped
+
+
+def test_mh_accept_rule_matches_explore_mh_novarpar():
+    """prjmh_temper_rf.f90:739-757: reject iff ran_uni >= EXP(logPr + (logL_new - logL)*beta_mh),
+    and always when the proposal left the prior bounds."""
+    g = torch.Generator().manual_seed(5)
+    n = 4096
+    cur = torch.randn(n, generator=g, dtype=torch.float64) * 20 - 50
+    new = cur + torch.randn(n, generator=g, dtype=torch.float64) * 3
+    beta = torch.rand(n, generator=g, dtype=torch.float64)
+    u = torch.rand(n, generator=g, dtype=torch.float64)
+    lpr = torch.randn(n, generator=g, dtype=torch.float64) * 0.1
+    out = torch.rand(n, generator=g) < 0.1
+    acc = tempering.mh_accept(cur, new, beta, u, logPr_new=lpr, outside=out)
+    for i in range(0, n, 7):
+        want = (not bool(out[i])) and not (float(u[i]) >= math.exp(float(lpr[i]) + (float(new[i]) - float(cur[i])) * float(beta[i])))
+        assert bool(acc[i]) == want
+    assert 0.2 < acc.double().mean() < 0.9
