@@ -87,3 +87,20 @@ def test_workloads_are_seeded_and_well_formed():
         assert np.all(np.diff(zz) >= 100.1 - 1e-9) and np.all(vp[b, :k[b]] >= 1500)
     so, sd = workloads.make_sources(64, 2)
     assert so.shape == sd.shape == (64,) and sd.min() >= 1050
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under raytracerfortran_b200/ (Python, C++, CUDA)
+    or include/ may import, link or mention it."""
+    pkg = os.path.join(ROOT, "raytracerfortran_b200")
+    offenders = []
+    for base in (pkg, os.path.join(ROOT, "include"), os.path.join(ROOT, "shim")):
+        for dirpath, _, files in os.walk(base):
+            for f in files:
+                if f.endswith((".py", ".cu", ".h", ".cuh", ".cpp", ".f90")):
+                    text = open(os.path.join(dirpath, f), errors="ignore").read()
+                    if re.search(r"\boracle\b|liboracle|raymod_oracle", text):
+                        offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out
