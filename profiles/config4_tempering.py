@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--replicas", type=int, default=64)
     ap.add_argument("--proposals", type=int, default=1024)
+    ap.add_argument("--host-swap", action="store_true", help="swap decisions on the host (numpy Philox)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -51,11 +52,10 @@ def main():
     logL = torch.empty((R, P), dtype=torch.float64, device=dev)
     cur = None
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
-    swaps = 0
-    t_eval = t_swap = 0.0
+    timers, nacc = [], []
 
     def one_step(step):
-        nonlocal cur, beta, swaps, t_eval, t_swap
+        nonlocal cur, beta
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
         tempering.evaluate_replicas(tk, tv, tz, ts, td, to, tg, logL=logL)
@@ -67,18 +67,22 @@ def main():
             acc = tempering.mh_accept(cur, new, beta, u)
             cur = torch.where(acc, new, cur)
         e1.record()
-        beta, st = tempering.tempering_swap_round(cur, beta, seed=2026, round_index=step)
+        if args.host_swap:
+            beta, st = tempering.tempering_swap_round(cur, beta, seed=2026, round_index=step)
+            acc = torch.from_numpy(st["accept"].astype(np.int64)).to(dev)
+        else:
+            beta, st = tempering.tempering_swap_round_device(cur, beta, seed=2026, round_index=step)
+            acc = st["accept"].to(torch.int64)
         e2.record()
-        torch.cuda.synchronize()
-        t_eval += e0.elapsed_time(e1)
-        t_swap += e1.elapsed_time(e2)
-        swaps += st["accepted"]
-        return st
+        timers.append((e0, e1, e2))
+        nacc.append(acc.sum())
+        return acc
 
     for w in range(3):
         one_step(w)
-    t_eval = t_swap = 0.0
-    swaps = 0
+    torch.cuda.synchronize()
+    timers.clear()
+    nacc.clear()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -88,9 +92,12 @@ def main():
         last = one_step(3 + s)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    t_eval = sum(a.elapsed_time(b) for a, b, _ in timers)
+    t_swap = sum(b.elapsed_time(c) for _, b, c in timers)
+    swaps = int(torch.stack(nacc).sum().item())
     # every rank derived the same decisions
     if world > 1:
-        mine = torch.tensor(last["accept"].astype(np.int64), device=dev)
+        mine = last.clone()
         ref = mine.clone()
         dist.broadcast(ref, 0)
         assert torch.equal(mine, ref), "swap decisions differ between ranks"
@@ -105,7 +112,8 @@ def main():
             "ms_per_step_evaluate": t_eval / args.steps, "ms_per_step_swap_round": t_swap / args.steps,
             "evals_per_s": evals / wall, "loglhood_per_s": args.replicas * P * args.steps / wall,
             "swap_allgather_bytes_per_rank": 16 * R, "swaps_accepted": swaps,
-            "swap_pairs_per_round": args.replicas // 2}))
+            "swap_pairs_per_round": args.replicas // 2,
+            "swap_decisions": "host (numpy Philox)" if args.host_swap else "device"}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -127,3 +127,35 @@ def mh_accept(logL_cur, logL_new, beta, u, logPr_new=None, outside=None):
     if outside is not None:
         accept = accept & ~outside.to(torch.bool)
     return accept
+
+
+def tempering_swap_round_device(logL_local, beta_local, seed, round_index, group=None):
+    """The swap round without leaving the device: all-gather, pairing, TEMPSWP_MH's accept rule
+    (prjmh_temper_rf.f90:1341-1344) and the beta exchange are tensor operations on the device the
+    replicas live on, so an MCMC step never synchronises with the host.  Every rank seeds an
+    identical device generator from (seed, round_index) and therefore derives the same pairs and
+    the same decisions.  Returns (new beta_local, info) where info holds device tensors
+    `pairs_i`, `pairs_j`, `accept`."""
+    dev = logL_local.device
+    n_local = logL_local.numel()
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    rank = dist.get_rank(group) if distributed else 0
+    mine = torch.stack([logL_local.to(torch.float64), beta_local.to(torch.float64)], dim=1).contiguous()
+    if distributed:
+        allr = torch.empty((dist.get_world_size(group) * n_local, 2), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine, group=group)
+    else:
+        allr = mine
+    logL, beta = allr[:, 0], allr[:, 1]
+    n = logL.numel()
+    g = torch.Generator(device=dev)
+    g.manual_seed((int(seed) * 1_000_003 + int(round_index)) & 0x7FFFFFFFFFFFFFFF)
+    perm = torch.randperm(n, generator=g, device=dev)
+    npair = n // 2
+    i, j = perm[:npair], perm[npair:2 * npair]
+    u = torch.rand(npair, generator=g, device=dev, dtype=torch.float64)
+    accept = u <= torch.exp((beta[j] - beta[i]) * (logL[i] - logL[j]))
+    new = beta.clone()
+    new[i] = torch.where(accept, beta[j], beta[i])
+    new[j] = torch.where(accept, beta[i], beta[j])
+    return new[rank * n_local:(rank + 1) * n_local].clone(), {"pairs_i": i, "pairs_j": j, "accept": accept}

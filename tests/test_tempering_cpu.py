@@ -68,7 +68,16 @@ def _worker(rank, world, port, ret):
         for rnd in range(5):
             beta, st = tempering.tempering_swap_round(logL, beta, seed, rnd)
             history.append((beta.numpy().copy(), st["accept"].copy(), st["pairs"].copy()))
+        # the all-device variant: same rule, device-side pairing; ranks must agree
+        beta_d = torch.from_numpy(beta_all[lo:hi].copy())
+        dev_hist = []
+        for rnd in range(5):
+            before = beta_d.clone()
+            beta_d, info = tempering.tempering_swap_round_device(logL, beta_d, seed, rnd)
+            dev_hist.append((before.numpy().copy(), beta_d.numpy().copy(), info["pairs_i"].numpy().copy(),
+                             info["pairs_j"].numpy().copy(), info["accept"].numpy().copy()))
         ret[rank] = history
+        ret[("dev", rank)] = dev_hist
     finally:
         dist.destroy_process_group()
 
@@ -90,6 +99,21 @@ def test_swap_round_world_size_2_gloo():
         assert np.array_equal(h0[rnd][2], pairs) and np.array_equal(h1[rnd][2], pairs)
         assert np.array_equal(np.concatenate([h0[rnd][0], h1[rnd][0]]), beta_all)      # same ladder
     assert sum(int(h0[r][1].sum()) for r in range(5)) > 0                              # something swapped
+    # device variant: both ranks derived the same pairs and decisions, betas stay a permutation,
+    # and the decisions follow TEMPSWP_MH's rule on the gathered state
+    d0, d1 = ret[("dev", 0)], ret[("dev", 1)]
+    ladder = tempering.temperature_ladder(8, 1.4)
+    for rnd in range(5):
+        b0, n0, i0, j0, a0 = d0[rnd]
+        b1, n1, i1, j1, a1 = d1[rnd]
+        assert np.array_equal(i0, i1) and np.array_equal(j0, j1) and np.array_equal(a0, a1)
+        before, after = np.concatenate([b0, b1]), np.concatenate([n0, n1])
+        assert sorted(after.tolist()) == sorted(ladder.tolist())
+        for i, j, a in zip(i0, j0, a0):
+            if a:
+                assert after[i] == before[j] and after[j] == before[i]
+            else:
+                assert after[i] == before[i] and after[j] == before[j]
 
 
 def test_mh_accept_rule_matches_explore_mh_novarpar():
