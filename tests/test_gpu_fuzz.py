@@ -79,3 +79,24 @@ def test_random_small_batches_many_shapes():
         got = rt.dff_batch(v, z, nl, so, sd, want_p=True)
         assert same(got["timeP"], ref["timeP"]), (trial, B, L, S)
         assert same(got["p"], ref["p"]), (trial, B, L, S)
+
+
+def test_extreme_shapes():
+    """Many sources for one model (hundreds of source chunks), and the deepest model the packed
+    ray word allows (254 interfaces)."""
+    v, z, nl = workloads.make_models(1, 12, 3)
+    so, sd = workloads.make_sources(70001, 3)
+    got = rt.dff(v[0], z[0], so, sd)
+    want, _, _ = oracle.trace_rays(v[0], z[0], so, sd)
+    assert same(got, want)
+    rng = np.random.default_rng(9)
+    B, L = 5, 254
+    vv = rng.uniform(1500, 10000, (B, L + 1))
+    zz = np.sort(rng.uniform(50, 10000, (B, L)), axis=1)
+    nn = np.array([254, 254, 200, 1, 77], dtype=np.int32)
+    so, sd = workloads.make_sources(40, 9, near_critical=True)
+    ref = oracle.dff_batch(vv, zz, nn, so, sd, want_p=True)
+    out = rt.dff_batch(vv, zz, nn, so, sd, want_p=True)
+    assert same(out["timeP"], ref["timeP"]) and same(out["p"], ref["p"])
+    with pytest.raises(rt.RayTraceError):
+        rt.dff_batch(np.ones((2, 300)), np.ones((2, 299)), np.array([10, 10], dtype=np.int32), so, sd)
