@@ -130,8 +130,11 @@ int         rtb200_init(int device);          /* optional; lazy init picks the d
 void        rtb200_shutdown(void);
 const char *rtb200_last_error(void);          /* "" when the last call succeeded               */
 int         rtb200_device_count(void);        /* 0 without a driver / device                   */
-/* options: "variant" (0 lock-step loops, 1 lane state machine), "threads", "tile_models",
- *          "tile_sources", "chunk_models", "ctas_per_sm"; <= 0 restores the default;
+/* options: "variant" (0 plain loops, 1 lane state machine, 3 deep-model kernel, < 0 by depth),
+ *          "threads", "tile_models", "tile_sources", "chunk_models", "ctas_per_sm"; <= 0 restores
+ *          the default; "comp_streams" (1: host-call chunks run on one compute stream; default 2:
+ *          consecutive chunks alternate between two so one chunk's tail overlaps the next);
+ *          "static_tiles" (1: CTAs stride over the tiles instead of claiming them from a counter);
  *          "logl_shuffle" (1: reduce the residuals of a model with a warp-shuffle tree instead of
  *          the reference's source order -- same terms, ~N ulp from the ordered sum; default 0) */
 int         rtb200_set_option(const char *name, double value);

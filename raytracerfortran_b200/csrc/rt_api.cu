@@ -24,6 +24,7 @@ using rtb::TileCfg;
 
 constexpr double kPi = 3.141592653589793238462643383279502884197;  // data_type.f90:5 (PI2)
 constexpr int    kMaxChunks = 64;
+constexpr int    kSchedSlots = 256;  // tile-scheduler counter pairs, one per launch in flight
 constexpr int    kDeepLdv = 40;     // models with this many velocities or more use the deep-model kernel
 
 struct DevBuf {
@@ -50,16 +51,17 @@ struct DevBuf {
 struct Ctx {
     bool inited = false, ok = false;
     int  device = 0, sms = 0, smem_optin = 0;
-    cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_comp = nullptr, s_comp2 = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t  ev_h2d[kMaxChunks], ev_k0[kMaxChunks], ev_k1[kMaxChunks];
     cudaEvent_t  ev_t0 = nullptr, ev_t1 = nullptr;
     DevBuf vels, depths, nl, off, dep, cosv, tobs, sigma, timeP, pout, logL, arena, voro, vsorted,
-        idxar, arparb;
+        idxar, arparb, sched;
+    unsigned sched_seq = 0;        // launches take scheduler slots round robin
     void  *pin = nullptr;          // pinned staging for small calls
     size_t pin_cap = 0;
     // options (<= 0: automatic)
     int opt_variant = -1, opt_threads = 0, opt_tile_models = 0, opt_tile_sources = 0,
-        opt_chunk_models = 0, opt_ctas = 0, opt_logl_shuffle = 0;
+        opt_chunk_models = 0, opt_ctas = 0, opt_logl_shuffle = 0, opt_comp_streams = 0, opt_static_tiles = 0;
     // stats
     double    kernel_ms = 0.0, total_ms = 0.0;
     long long launches = 0;
@@ -119,6 +121,7 @@ int ensure_init(int device = -1) {
     g.sms = prop.multiProcessorCount;
     CK(cudaDeviceGetAttribute(&g.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, g.device));
     CK(cudaStreamCreateWithFlags(&g.s_comp, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.s_comp2, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.s_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.s_d2h, cudaStreamNonBlocking));
     for (int i = 0; i < kMaxChunks; ++i) {
@@ -128,12 +131,20 @@ int ensure_init(int device = -1) {
     }
     CK(cudaEventCreate(&g.ev_t0));
     CK(cudaEventCreate(&g.ev_t1));
+    CK(g.sched.reserve(kSchedSlots * 2 * sizeof(int)));
+    CK(cudaMemset(g.sched.p, 0, kSchedSlots * 2 * sizeof(int)));
     g.ok = true;
     g.err.clear();
     return 0;
 }
 
 int even_up(int x) { return (x + 1) & ~1; }
+
+// Counter pair for one launch's dynamic tile scheduling (the kernel leaves it zeroed).
+int *next_sched() {
+    if (g.opt_static_tiles) return nullptr;
+    return g.sched.as<int>() + 2 * (g.sched_seq++ % kSchedSlots);
+}
 
 // Tile geometry for one launch (DESIGN.md "tiling").
 int choose_cfg(int B, int ldv, int ldz, int nsrc, bool aligned, TileCfg &c) {
@@ -262,6 +273,7 @@ int run_host_small(const HostCall &h, const TileCfg &cfg, int ldz) {
     a.logc = h.logL ? log_norm_const(h.nsrc) : 0.0;
     a.padded = 1;
     CK(cudaEventRecord(g.ev_k0[0], st));
+    a.sched = next_sched();
     CK(rtb::launch_batch(a, cfg, st));
     CK(cudaEventRecord(g.ev_k1[0], st));
     g.launches++;
@@ -322,8 +334,14 @@ int run_host(const HostCall &h) {
                                 h.nsrc, g.s_h2d));
     g.launches++;
 
-    // chunk boundaries are multiples of the tile size
-    size_t chunk = g.opt_chunk_models > 0 ? (size_t)g.opt_chunk_models : (size_t)65536;
+    // Chunk boundaries are multiples of the tile size.  The default chunk is a whole number of
+    // waves of the persistent grid (every CTA gets the same number of tiles), and consecutive
+    // chunks alternate between two compute streams so the first CTAs of chunk j+1 take the SM
+    // slots the last CTAs of chunk j leave instead of waiting for the whole grid to drain.
+    const size_t wave = (size_t)g.sms * g.last_ctas * cfg.M;
+    size_t chunk = g.opt_chunk_models > 0 ? (size_t)g.opt_chunk_models
+                                          : std::max<size_t>(1, (65536 + wave / 2) / wave) * wave;
+    const int ncomp = g.opt_comp_streams == 1 ? 1 : 2;
     chunk = std::max(chunk, (B + kMaxChunks - 1) / kMaxChunks);
     chunk = (chunk + cfg.M - 1) / cfg.M * cfg.M;
     const int nchunks = (int)((B + chunk - 1) / chunk);
@@ -369,10 +387,12 @@ int run_host(const HostCall &h) {
         TileCfg cj = cfg;
         const int ntiles = (int)((nb + cfg.M - 1) / cfg.M);
         cj.grid = std::max(1, std::min(ntiles, g.sms * g.last_ctas));
-        CK(cudaStreamWaitEvent(g.s_comp, g.ev_h2d[j], 0));
-        CK(cudaEventRecord(g.ev_k0[j], g.s_comp));
-        CK(rtb::launch_batch(a, cj, g.s_comp));
-        CK(cudaEventRecord(g.ev_k1[j], g.s_comp));
+        cudaStream_t sc = (j % ncomp) ? g.s_comp2 : g.s_comp;
+        CK(cudaStreamWaitEvent(sc, g.ev_h2d[j], 0));
+        CK(cudaEventRecord(g.ev_k0[j], sc));
+        a.sched = next_sched();
+        CK(rtb::launch_batch(a, cj, sc));
+        CK(cudaEventRecord(g.ev_k1[j], sc));
         g.launches++;
         g.last = cj;
 
@@ -389,6 +409,7 @@ int run_host(const HostCall &h) {
     CK(cudaEventRecord(g.ev_t1, g.s_d2h));
     CK(cudaStreamSynchronize(g.s_d2h));
     CK(cudaStreamSynchronize(g.s_comp));
+    CK(cudaStreamSynchronize(g.s_comp2));
     for (int j = 0; j < nchunks; ++j) {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, g.ev_k0[j], g.ev_k1[j]));
@@ -598,6 +619,7 @@ int loglhood_batch_voro(const int *k, const double *voro, const int *B, const in
     a.logc = log_norm_const(ns);
     a.padded = 1;
     CK(cudaEventRecord(g.ev_k0[0], st));
+    a.sched = next_sched();
     CK(rtb::launch_batch(a, cfg, st));
     CK(cudaEventRecord(g.ev_k1[0], st));
     g.launches += 3;
@@ -634,6 +656,7 @@ int rtb200_dff_batch_device(const double *d_vels, const double *d_depths, const 
     a.timeP = d_timeP; a.p_out = d_p_out; a.logL = d_logL;
     a.logc = d_logL ? log_norm_const(NSrc) : 0.0;
     CK(cudaEventRecord(g.ev_k0[0], st));
+    a.sched = next_sched();
     CK(rtb::launch_batch(a, cfg, st));
     CK(cudaEventRecord(g.ev_k1[0], st));
     g.launches += 2;
@@ -657,7 +680,8 @@ void rtb200_shutdown(void) {
     g.pin = nullptr;
     g.pin_cap = 0;
     for (DevBuf *b : {&g.vels, &g.depths, &g.nl, &g.off, &g.dep, &g.cosv, &g.tobs, &g.sigma,
-                      &g.timeP, &g.pout, &g.logL, &g.arena, &g.voro, &g.vsorted, &g.idxar, &g.arparb})
+                      &g.timeP, &g.pout, &g.logL, &g.arena, &g.voro, &g.vsorted, &g.idxar, &g.arparb,
+                      &g.sched})
         b->release();
     for (int i = 0; i < kMaxChunks; ++i) {
         cudaEventDestroy(g.ev_h2d[i]);
@@ -667,6 +691,7 @@ void rtb200_shutdown(void) {
     cudaEventDestroy(g.ev_t0);
     cudaEventDestroy(g.ev_t1);
     cudaStreamDestroy(g.s_comp);
+    cudaStreamDestroy(g.s_comp2);
     cudaStreamDestroy(g.s_h2d);
     cudaStreamDestroy(g.s_d2h);
     g.inited = g.ok = false;
@@ -688,6 +713,8 @@ int rtb200_set_option(const char *name, double value) {
     else if (!strcmp(name, "tile_sources")) g.opt_tile_sources = v;
     else if (!strcmp(name, "chunk_models")) g.opt_chunk_models = v;
     else if (!strcmp(name, "ctas_per_sm")) g.opt_ctas = v;
+    else if (!strcmp(name, "comp_streams")) g.opt_comp_streams = v;
+    else if (!strcmp(name, "static_tiles")) g.opt_static_tiles = v > 0 ? 1 : 0;
     else if (!strcmp(name, "logl_shuffle")) g.opt_logl_shuffle = v > 0 ? 1 : 0;
     else return -1;
     return 0;

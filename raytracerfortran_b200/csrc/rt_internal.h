@@ -38,6 +38,9 @@ struct BatchArgs {
     const int    *idxar;       // [B] or null: obj%idxarRT(1), 1 = apply the AR model to this state
     const double *arpar;       // [B] obj%arparRT(1)
     double        armx;        // armxRT: |DarRT| beyond it rejects the state (logL = -HUGE)
+    // dynamic tile scheduling: [0] tiles claimed beyond the first wave, [1] CTAs finished; both
+    // zero between launches (the last CTA resets them); null = static stride
+    int          *sched;
 };
 
 // Tile geometry chosen by the host for one launch.

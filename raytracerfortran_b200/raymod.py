@@ -78,7 +78,8 @@ def dff_batch(vels, depths, nlayers, src_offset, src_depth, tobs=None, sigma=Non
     B, nsrc = v.shape[0], so.size
     if nl.size != B or sd.size != nsrc:
         raise ValueError("nlayers / source sizes do not match")
-    if B and (nl.max() + 1 > v.shape[1] or nl.max() > max(z.shape[1], 0)):
+    nl_max = int(nl.max()) if B else 0
+    if nl_max + 1 > v.shape[1] or nl_max > max(z.shape[1], 0):
         raise ValueError("nlayers exceeds the row length of vels / depths")
     t = out_times if out_times is not None else (np.empty((B, nsrc)) if want_times else None)
     p = out_p if out_p is not None else (np.empty((B, nsrc)) if want_p else None)
