@@ -38,11 +38,17 @@ def assert_logl_close(got, want, nsrc, sigma):
     assert np.array_equal(got[~fin], want[~fin])
 
 
+def _reset_options():
+    for name in ("variant", "threads", "tile_models", "tile_sources", "chunk_models", "ctas_per_sm",
+                 "comp_streams", "static_tiles"):
+        rt.set_option(name, -1 if name == "variant" else 0)
+
+
 @pytest.fixture(autouse=True)
 def _defaults():
-    for name in ("variant", "threads", "tile_models", "tile_sources", "chunk_models", "ctas_per_sm"):
-        rt.set_option(name, -1 if name == "variant" else 0)
+    _reset_options()
     yield
+    _reset_options()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -196,6 +202,29 @@ def test_ragged_batches_and_chunking(variant):
         assert_bitexact(got["timeP"], ref["timeP"], f"timeP {opts}")
         assert_bitexact(got["p"], ref["p"], f"p {opts}")
         assert_logl_close(got["logL"], ref["logL"], nsrc, sigma)
+
+
+@pytest.mark.parametrize("variant", [1, 3])
+def test_tile_scheduling_and_host_pipeline_options(variant):
+    """Many more tiles than persistent CTAs: tiles claimed from the global counter (repeated
+    launches reuse counter slots the kernel must leave zeroed), the static stride, and the host
+    pipeline on one or two compute streams all give the oracle's bits."""
+    rt.set_option("variant", variant)
+    B, nsrc = 24000, 16
+    v, z, nl = workloads.make_models(B, 10, 31)
+    so, sd = workloads.make_sources(nsrc, 31)
+    tobs, sigma = workloads.make_observations(np.ones(nsrc), B, 31)
+    ref = oracle.dff_batch(v, z, nl, so, sd, tobs=tobs, sigma=sigma)
+    for opts in ({"tile_models": 4}, {"tile_models": 4}, {"tile_models": 4, "static_tiles": 1},
+                 {"tile_models": 4, "static_tiles": 0, "chunk_models": 1000, "comp_streams": 1},
+                 {"tile_models": 8, "chunk_models": 1000, "comp_streams": 2}):
+        for k_, v_ in opts.items():
+            rt.set_option(k_, v_)
+        for _ in range(3):
+            got = rt.dff_batch(v, z, nl, so, sd, tobs=tobs, sigma=sigma)
+            assert_bitexact(got["timeP"], ref["timeP"], f"timeP {opts}")
+            assert_logl_close(got["logL"], ref["logL"], nsrc, sigma)
+    assert rt.get_stat("grid") < B // 8          # the tiles did outnumber the CTAs
 
 
 def test_empty_and_single():
