@@ -118,10 +118,26 @@ def cpu_leg(v, z, nl, so, sd, tobs, sigma, budget_s=12.0):
     out = oracle.dff_batch(v[:n], z[:n], nl[:n], so, sd, tobs=tobs, sigma=sigma[:n],
                            want_times=False, nthreads=ncpu)
     dt = time.perf_counter() - t0
+    # also one core, and the faithful call pattern (one model per call through the
+    # 8-argument entry, which truncates ./rays.dat on every call, subroutineR-quiet.f90:432-433)
+    n1 = int(min(n, max(500, rate / ncpu * 1.5)))
+    t0 = time.perf_counter()
+    oracle.dff_batch(v[:n1], z[:n1], nl[:n1], so, sd, tobs=tobs, sigma=sigma[:n1], want_times=False,
+                     nthreads=1)
+    dt1 = time.perf_counter() - t0
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        t0 = time.perf_counter()
+        oracle.dff_batch_faithful(v[:n1], z[:n1], nl[:n1], so, sd, os.path.join(tmp, "rays.dat"))
+        dtf = time.perf_counter() - t0
     return {"value": n * len(so) / dt, "unit": UNIT, "cores": int(out["threads"]), "kind": "port",
             "sample": f"first {n} of {len(v)} models x {len(so)} sources, fused logL, {dt:.2f} s; "
                       "C restatement of the gfortran path (gcc -O2 -ffp-contract=off, OpenMP), "
-                      "no per-call rays.dat truncation"}, n, dt
+                      "no per-call rays.dat truncation",
+            "single_core": {"value": n1 * len(so) / dt1, "sample": f"{n1} models, {dt1:.2f} s"},
+            "faithful_single_core": {"value": n1 * len(so) / dtf,
+                                     "sample": f"{n1} models, one dff call per model with the "
+                                               f"per-call rays.dat truncate, {dtf:.2f} s"}}, n, dt
 
 
 def run_reference(args, rank):

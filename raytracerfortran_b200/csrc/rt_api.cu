@@ -54,9 +54,10 @@ struct Ctx {
     cudaStream_t s_comp = nullptr, s_comp2 = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t  ev_h2d[kMaxChunks], ev_k0[kMaxChunks], ev_k1[kMaxChunks];
     cudaEvent_t  ev_t0 = nullptr, ev_t1 = nullptr;
-    DevBuf vels, depths, nl, off, dep, cosv, tobs, sigma, timeP, pout, logL, arena, voro, vsorted,
+    DevBuf vels, depths, nl, off, dep, tobs, sigma, timeP, pout, logL, arena, voro, vsorted,
         idxar, arparb, sched;
     unsigned sched_seq = 0;        // launches take scheduler slots round robin
+    bool     sched_dirty = false;  // a CUDA call failed: a kernel may have left counters behind
     void  *pin = nullptr;          // pinned staging for small calls
     size_t pin_cap = 0;
     // options (<= 0: automatic)
@@ -76,6 +77,7 @@ Ctx g;
 int fail(const std::string &what, cudaError_t e = cudaSuccess) {
     g.err = what;
     if (e != cudaSuccess) {
+        g.sched_dirty = true;
         g.err += ": ";
         g.err += cudaGetErrorString(e);
     }
@@ -143,6 +145,11 @@ int even_up(int x) { return (x + 1) & ~1; }
 // Counter pair for one launch's dynamic tile scheduling (the kernel leaves it zeroed).
 int *next_sched() {
     if (g.opt_static_tiles) return nullptr;
+    if (g.sched_dirty) {
+        cudaDeviceSynchronize();
+        if (cudaMemset(g.sched.p, 0, kSchedSlots * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+        g.sched_dirty = false;
+    }
     return g.sched.as<int>() + 2 * (g.sched_seq++ % kSchedSlots);
 }
 
@@ -263,7 +270,6 @@ int run_host_small(const HostCall &h, const TileCfg &cfg, int ldz) {
     a.B = h.B; a.ldv = h.ldv; a.ldz = ldz; a.kmode = h.kmode;
     a.src_offset = reinterpret_cast<double *>(dp + o_off);
     a.src_depth = reinterpret_cast<double *>(dp + o_dep);
-    a.src_cos = nullptr;
     a.tobs = h.tobs ? reinterpret_cast<double *>(dp + o_obs) : nullptr;
     a.nsrc = h.nsrc;
     a.sigma = h.sigma ? reinterpret_cast<double *>(dp + o_sig) : nullptr;
@@ -315,7 +321,6 @@ int run_host(const HostCall &h) {
     CK(g.nl.reserve(Bpad * 4));
     CK(g.off.reserve(S * 8));
     CK(g.dep.reserve(S * 8));
-    CK(g.cosv.reserve(S * 8));
     if (h.tobs) CK(g.tobs.reserve(S * 8));
     if (h.sigma) CK(g.sigma.reserve(B * 8));
     if (h.timeP) CK(g.timeP.reserve(B * S * 8));
@@ -330,9 +335,6 @@ int run_host(const HostCall &h) {
     CK(cudaMemcpyAsync(g.off.p, h.off, S * 8, cudaMemcpyHostToDevice, g.s_h2d));
     CK(cudaMemcpyAsync(g.dep.p, h.dep, S * 8, cudaMemcpyHostToDevice, g.s_h2d));
     if (h.tobs) CK(cudaMemcpyAsync(g.tobs.p, h.tobs, S * 8, cudaMemcpyHostToDevice, g.s_h2d));
-    CK(rtb::launch_prep_sources(g.off.as<double>(), g.dep.as<double>(), g.cosv.as<double>(),
-                                h.nsrc, g.s_h2d));
-    g.launches++;
 
     // Chunk boundaries are multiples of the tile size.  The default chunk is a whole number of
     // waves of the persistent grid (every CTA gets the same number of tiles), and consecutive
@@ -373,7 +375,7 @@ int run_host(const HostCall &h) {
         a.nlayers = g.nl.as<int>() + j0;
         a.B = (int)nb; a.ldv = h.ldv; a.ldz = ldz; a.kmode = h.kmode;
         a.src_offset = g.off.as<double>(); a.src_depth = g.dep.as<double>();
-        a.src_cos = g.cosv.as<double>(); a.tobs = h.tobs ? g.tobs.as<double>() : nullptr;
+        a.tobs = h.tobs ? g.tobs.as<double>() : nullptr;
         a.nsrc = h.nsrc;
         a.sigma = h.sigma ? g.sigma.as<double>() + j0 : nullptr;
         a.timeP = h.timeP ? g.timeP.as<double>() + j0 * S : nullptr;
@@ -597,7 +599,7 @@ int loglhood_batch_voro(const int *k, const double *voro, const int *B, const in
     CK(g.vels.reserve(Bpad * ld * 8));
     CK(g.depths.reserve(Bpad * ld * 8));
     CK(g.nl.reserve(Bpad * 4));
-    CK(g.off.reserve(S * 8)); CK(g.dep.reserve(S * 8)); CK(g.cosv.reserve(S * 8)); CK(g.tobs.reserve(S * 8));
+    CK(g.off.reserve(S * 8)); CK(g.dep.reserve(S * 8)); CK(g.tobs.reserve(S * 8));
     CK(g.sigma.reserve(Bz * 8)); CK(g.logL.reserve(Bz * 8));
     if (tpred) CK(g.timeP.reserve(Bz * S * 8));
     cudaStream_t st = g.s_comp;
@@ -607,13 +609,12 @@ int loglhood_batch_voro(const int *k, const double *voro, const int *B, const in
     CK(cudaMemcpyAsync(g.dep.p, src_depth, S * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(g.tobs.p, tobs, S * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(g.sigma.p, sigma, Bz * 8, cudaMemcpyHostToDevice, st));
-    CK(rtb::launch_prep_sources(g.off.as<double>(), g.dep.as<double>(), g.cosv.as<double>(), ns, st));
     CK(rtb::launch_prep_voro(g.nl.as<int>(), g.voro.as<double>(), nb, ld, g.vels.as<double>(),
                              g.depths.as<double>(), voro_sorted ? g.vsorted.as<double>() : nullptr, st));
     BatchArgs a{};
     a.vels = g.vels.as<double>(); a.depths = g.depths.as<double>(); a.nlayers = g.nl.as<int>();
     a.B = nb; a.ldv = ld; a.ldz = ld; a.kmode = 1;
-    a.src_offset = g.off.as<double>(); a.src_depth = g.dep.as<double>(); a.src_cos = g.cosv.as<double>();
+    a.src_offset = g.off.as<double>(); a.src_depth = g.dep.as<double>();
     a.tobs = g.tobs.as<double>(); a.nsrc = ns; a.sigma = g.sigma.as<double>();
     a.timeP = tpred ? g.timeP.as<double>() : nullptr; a.p_out = nullptr; a.logL = g.logL.as<double>();
     a.logc = log_norm_const(ns);
@@ -622,7 +623,7 @@ int loglhood_batch_voro(const int *k, const double *voro, const int *B, const in
     a.sched = next_sched();
     CK(rtb::launch_batch(a, cfg, st));
     CK(cudaEventRecord(g.ev_k1[0], st));
-    g.launches += 3;
+    g.launches += 2;
     g.last = cfg;
     CK(cudaMemcpyAsync(logL, g.logL.p, Bz * 8, cudaMemcpyDeviceToHost, st));
     if (tpred) CK(cudaMemcpyAsync(tpred, g.timeP.p, Bz * S * 8, cudaMemcpyDeviceToHost, st));
@@ -646,12 +647,10 @@ int rtb200_dff_batch_device(const double *d_vels, const double *d_depths, const 
     TileCfg cfg;
     const bool al = aligned16(d_vels) && aligned16(d_depths);
     if (int rc = choose_cfg(B, ldv, std::max(ldz, 0), NSrc, al, cfg)) return rc;
-    CK(g.cosv.reserve((size_t)NSrc * 8));
-    CK(rtb::launch_prep_sources(d_src_offset, d_src_depth, g.cosv.as<double>(), NSrc, st));
     BatchArgs a{};
     a.vels = d_vels; a.depths = d_depths; a.nlayers = d_nlayers;
     a.B = B; a.ldv = ldv; a.ldz = std::max(ldz, 0); a.kmode = kmode;
-    a.src_offset = d_src_offset; a.src_depth = d_src_depth; a.src_cos = g.cosv.as<double>();
+    a.src_offset = d_src_offset; a.src_depth = d_src_depth;
     a.tobs = d_tobs; a.nsrc = NSrc; a.sigma = d_sigma;
     a.timeP = d_timeP; a.p_out = d_p_out; a.logL = d_logL;
     a.logc = d_logL ? log_norm_const(NSrc) : 0.0;
@@ -659,7 +658,7 @@ int rtb200_dff_batch_device(const double *d_vels, const double *d_depths, const 
     a.sched = next_sched();
     CK(rtb::launch_batch(a, cfg, st));
     CK(cudaEventRecord(g.ev_k1[0], st));
-    g.launches += 2;
+    g.launches++;
     g.last = cfg;
     if (!stream) {
         CK(cudaStreamSynchronize(st));
@@ -679,7 +678,7 @@ void rtb200_shutdown(void) {
     if (g.pin) cudaFreeHost(g.pin);
     g.pin = nullptr;
     g.pin_cap = 0;
-    for (DevBuf *b : {&g.vels, &g.depths, &g.nl, &g.off, &g.dep, &g.cosv, &g.tobs, &g.sigma,
+    for (DevBuf *b : {&g.vels, &g.depths, &g.nl, &g.off, &g.dep, &g.tobs, &g.sigma,
                       &g.timeP, &g.pout, &g.logL, &g.arena, &g.voro, &g.vsorted, &g.idxar, &g.arparb,
                       &g.sched})
         b->release();

@@ -25,7 +25,6 @@ struct BatchArgs {
     int           kmode;       // LOGLHOOD_RT model mapping (loglhood.f90:127-146)
     const double *src_offset;  // [nsrc]
     const double *src_depth;   // [nsrc]
-    const double *src_cos;     // [nsrc]  depth / sqrt(offset^2 + depth^2), from prep_sources
     const double *tobs;        // [nsrc] or null
     int           nsrc;
     const double *sigma;       // [B] or null
@@ -58,8 +57,6 @@ struct TileCfg {
 };
 
 size_t      tile_smem_bytes(const TileCfg &c, int ldv, int ldz);
-cudaError_t launch_prep_sources(const double *off, const double *dep, double *cosv, int nsrc,
-                                cudaStream_t st);
 cudaError_t launch_batch(const BatchArgs &a, const TileCfg &c, cudaStream_t st);
 cudaError_t launch_prep_voro(const int *k, const double *voro, int B, int ldk, double *vels,
                              double *depths, double *sorted, cudaStream_t st);
