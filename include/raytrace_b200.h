@@ -123,6 +123,32 @@ int rtb200_dff_batch_device(const double *d_vels, const double *d_depths, const 
                             double *d_timeP, const double *d_tobs, const double *d_sigma,
                             double *d_logL, double *d_p_out, int kmode, void *stream);
 
+/* One fixed-dimension Metropolis-Hastings move of B independent chains, entirely on the device:
+ * PROPOSAL (prjmh_temper_rf.f90:1386-1447, ENOS = 0: Cauchy step on voro(ivo,iwhich), |.| for a
+ * depth) -> INTERPLAYER_novar (loglhood.f90:214-295) -> CHECKBOUNDS2 (:1681-1716) -> LOGLHOOD ->
+ * the accept test of EXPLORE_MH_NOVARPAR (:739-757: reject iff ran_uni >= EXP(logPr + (logL_new -
+ * logL)*beta_mh), logPr = 0; proposals outside the prior bounds are rejected unevaluated).
+ * The random numbers are inputs, so the caller owns the generator.  Device pointers:
+ *   d_k      [B]          node counts (unchanged: no birth/death)
+ *   d_voro   [B][2][ldk]  current states, sorted by depth (row 0 depth, row 1 vp); accepted
+ *                         proposals are written back
+ *   d_logL   [B]          current logL; updated on accept
+ *   d_ivo, d_iwhich [B]   1-based node and parameter (1 = depth, 2 = vp) to perturb; ivo > k,
+ *                         or (ivo, iwhich) = (1, 1) (the fixed top node, :730) is a no-op (-1)
+ *   d_cauchy [B]          TAN(PI*(ran_uni - 0.5)) deviates;  d_uacc [B] uniforms of the accept test
+ *   d_beta   [B]          1/T of each chain;  d_sigma [B] sdparRT
+ *   prior    HOST [7]     fact/factor*pertsd(1), fact/factor*pertsd(2), minlim(1), minlim(2),
+ *                         maxlim(1), maxlim(2), hmin          (read_input.f90:207-214)
+ *   d_accept [B] out      1 accepted, 0 rejected, -1 rejected because outside the bounds
+ * Asynchronous on `stream` like rtb200_dff_batch_device; the library's scratch buffers are reused
+ * by consecutive calls, so issue them on one stream. */
+int rtb200_mh_step_device(const int *d_k, double *d_voro, double *d_logL, int B, int ldk,
+                          const int *d_ivo, const int *d_iwhich, const double *d_cauchy,
+                          const double *d_uacc, const double *d_beta, const double *d_sigma,
+                          const double *prior, const double *d_src_offset,
+                          const double *d_src_depth, const double *d_tobs, int NSrc,
+                          int *d_accept, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Runtime control and introspection
  * ---------------------------------------------------------------------------------------- */

@@ -70,6 +70,9 @@ def lib():
         _lib.orc_loglhood_voro.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, dp, C.c_double, dp, dp, dp]
         _lib.orc_loglhood_from_times_ar.restype = C.c_double
         _lib.orc_loglhood_from_times_ar.argtypes = [dp, dp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]
+        _lib.orc_mh_step_batch.restype = None
+        _lib.orc_mh_step_batch.argtypes = [ip, dp, dp, C.c_int, C.c_int, ip, ip, dp, dp, dp, dp, dp,
+                                           dp, dp, C.c_int, dp, ip, dp, dp]
         _lib.orc_batch_stats.restype = None
         _lib.orc_batch_stats.argtypes = [dp, dp, ip, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int,
                                          C.POINTER(Stats)]
@@ -119,6 +122,30 @@ def loglhood_rt(vp, ziface, src_offset, src_depth, tobs, sigma):
     ll = lib().orc_loglhood_rt(v.size, _p(v), _p(z) if z.size else None, _p(so), _p(sd), so.size,
                                _p(ob), float(sigma), _p(pred))
     return ll, pred
+
+
+def mh_step_batch(k, voro, logL, ivo, iwhich, cauchy, u_acc, beta, sigma, prior,
+                  src_offset, src_depth, tobs):
+    """One fixed-dimension MH move of B independent chains (orc_mh_step_batch).  voro [B, 2, ldk]
+    and logL [B] are the current states; returns a dict with the updated copies, `accept` [B]
+    (1 / 0 / -1 outside), the sorted proposals `voro_prop` and their `logL_prop` (NaN if outside)."""
+    kk = np.ascontiguousarray(k, dtype=np.int32)
+    vo = np.array(voro, dtype=np.float64, order="C", copy=True)
+    ll = np.array(logL, dtype=np.float64, copy=True)
+    B, two, ldk = vo.shape
+    assert two == 2
+    iv = np.ascontiguousarray(ivo, dtype=np.int32)
+    iw = np.ascontiguousarray(iwhich, dtype=np.int32)
+    so, sd, ob = _d(src_offset), _d(src_depth), _d(tobs)
+    acc = np.zeros(B, dtype=np.int32)
+    prop = vo.copy()
+    llp = np.full(B, np.nan)
+    I = C.POINTER(C.c_int)
+    lib().orc_mh_step_batch(kk.ctypes.data_as(I), _p(vo), _p(ll), B, ldk, iv.ctypes.data_as(I),
+                            iw.ctypes.data_as(I), _p(_d(cauchy)), _p(_d(u_acc)), _p(_d(beta)),
+                            _p(_d(sigma)), _p(_d(prior)), _p(so), _p(sd), so.size, _p(ob),
+                            acc.ctypes.data_as(I), _p(prop), _p(llp))
+    return {"voro": vo, "logL": ll, "accept": acc, "voro_prop": prop, "logL_prop": llp}
 
 
 def loglhood_voro(node_depth, node_vp, src_offset, src_depth, tobs, sigma):

@@ -501,6 +501,90 @@ double orc_loglhood_voro(int k, const double *node_depth, const double *node_vp,
     return ll;
 }
 
+/* ---- "next" rows N1 + N2: one fixed-dimension Metropolis-Hastings move of one chain ---- *
+ * The body of EXPLORE_MH_NOVARPAR's sweep for one (ivo, iwhich) (prjmh_temper_rf.f90:725-757):
+ * PROPOSAL (:1386-1447, ENOS = 0: Cauchy step on voro(ivo,iwhich), |.| for the depth, then
+ * INTERPLAYER_novar), CHECKBOUNDS2 (:1681-1716), LOGLHOOD, and the accept test
+ * "reject iff ran_uni >= EXP(logPr + (logL_new - logL)*beta_mh)" (:742-751).
+ * The random numbers are inputs: `cauchy` = TAN(PI*(ran_uni-0.5)), `u_acc` = ran_uni of :746.
+ * prior = { fact/factor*pertsd(1), fact/factor*pertsd(2), minlim(1), minlim(2), maxlim(1),
+ *           maxlim(2), hmin }  (read_input.f90:207-214, rjmcmc_com.f90:80).
+ * node_depth/node_vp [k] are the chain's sorted nodes (in/out), *logL its current logL (in/out).
+ * prop_depth/prop_vp [k] (may be NULL) receive the proposal after INTERPLAYER_novar, *logL_prop
+ * (may be NULL) its logL (untouched when outside).  Returns 1 accepted, 0 rejected, -1 rejected
+ * because the proposal left the prior bounds (ioutside).                                     */
+int orc_mh_step(int k, double *node_depth, double *node_vp, double *logL,
+                int ivo, int iwhich, double cauchy, double u_acc, double beta, double sigma,
+                const double *prior,
+                const double *src_offset, const double *src_depth, int nsrc, const double *tobs,
+                double *prop_depth, double *prop_vp, double *logL_prop)
+{
+    const double scale[2] = {prior[0], prior[1]}, minlim[2] = {prior[2], prior[3]},
+                 maxlim[2] = {prior[4], prior[5]}, hmin = prior[6];
+    if (k < 1 || ivo < 1 || ivo > k || iwhich < 1 || iwhich > 2 || (ivo == 1 && iwhich == 1))
+        return -1;                                               /* :730 CYCLE: nothing to propose */
+    double *d = (double *)malloc(sizeof(double) * (size_t)(2 * k + 2));
+    double *v = d + k + 1;
+    memcpy(d, node_depth, sizeof(double) * (size_t)k);
+    memcpy(v, node_vp, sizeof(double) * (size_t)k);
+    double *tgt = (iwhich == 1) ? d : v;
+    tgt[ivo - 1] = tgt[ivo - 1] + scale[iwhich - 1] * cauchy;    /* :1405 / :1416 */
+    if (iwhich == 1) d[ivo - 1] = fabs(d[ivo - 1]);              /* :1441-1443 */
+    int ordered = 1;
+    for (int i = 0; i < k; ++i) ordered = ordered && (d[i] == d[i]);
+    if (ordered) orc_interplayer_novar(k, d, v);                 /* :1444 */
+    if (prop_depth) memcpy(prop_depth, d, sizeof(double) * (size_t)k);
+    if (prop_vp) memcpy(prop_vp, v, sizeof(double) * (size_t)k);
+    /* CHECKBOUNDS2: ziface(i) = voro(i+1,1), hiface(1) = ziface(1), hiface(i) = ziface(i)-ziface(i-1) */
+    int outside = 0;
+    for (int ilay = 1; ilay <= k - 1; ++ilay) {
+        const double zi = d[ilay];
+        const double hi = (ilay == 1) ? zi : zi - d[ilay - 1];
+        if (hmin > hi) outside = 1;                              /* :1693 */
+        if (maxlim[0] < zi) outside = 1;                         /* :1694 */
+    }
+    if (ivo > 1 && (d[ivo - 1] < 0.0 || d[ivo - 1] > maxlim[0])) outside = 1;      /* :1698-1704 */
+    {
+        const double x = (iwhich == 1) ? d[ivo - 1] : v[ivo - 1];                 /* :1705-1712 */
+        if ((x - minlim[iwhich - 1]) < 0.0 || (maxlim[iwhich - 1] - x) < 0.0) outside = 1;
+    }
+    int ret;
+    if (outside) {
+        ret = -1;                                                /* :753-757 */
+    } else {
+        const double ll = orc_loglhood_rt(k, v, d + 1, src_offset, src_depth, nsrc, tobs, sigma, NULL);
+        if (logL_prop) *logL_prop = ll;
+        const double logPLratio = 0.0 + (ll - *logL) * beta;     /* :744-745, logPr = 0 (ENOS = 0) */
+        if (u_acc >= exp(logPLratio)) {
+            ret = 0;                                             /* :747-749 */
+        } else {
+            memcpy(node_depth, d, sizeof(double) * (size_t)k);   /* :750 obj = objnew1 */
+            memcpy(node_vp, v, sizeof(double) * (size_t)k);
+            *logL = ll;
+            ret = 1;
+        }
+    }
+    free(d);
+    return ret;
+}
+
+/* B independent chains, one move each; voro [B][2][ldk] (depth row, vp row), OpenMP over chains. */
+void orc_mh_step_batch(const int *k, double *voro, double *logL, int B, int ldk,
+                       const int *ivo, const int *iwhich, const double *cauchy, const double *u_acc,
+                       const double *beta, const double *sigma, const double *prior,
+                       const double *src_offset, const double *src_depth, int nsrc,
+                       const double *tobs, int *accept, double *voro_prop, double *logL_prop)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int b = 0; b < B; ++b) {
+        double *row = voro + (size_t)b * 2 * ldk;
+        double *pr = voro_prop ? voro_prop + (size_t)b * 2 * ldk : NULL;
+        accept[b] = orc_mh_step(k[b], row, row + ldk, &logL[b], ivo[b], iwhich[b], cauchy[b],
+                                u_acc[b], beta[b], sigma[b], prior, src_offset, src_depth, nsrc,
+                                tobs, pr, pr ? pr + ldk : NULL, logL_prop ? &logL_prop[b] : NULL);
+    }
+}
+
 /* ---- "next" row N4: the AR(1) residual error model of IAR = 1 ------------------------ *
  * ll:171-182: DarRT from ARPRED_RT (ll:616-653, order 1: DarRT(i) = arpar*DresRT(i-1) for
  * 1 < i < N, 0 at both ends), DresRT = DresRT - DarRT, CHECKBOUNDS_ARMXRT (ll:678-699) rejects

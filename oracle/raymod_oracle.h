@@ -103,6 +103,20 @@ double orc_loglhood_voro(int k, const double *node_depth, const double *node_vp,
                          const double *tobs, double sigma, double *tpred,
                          double *sorted_depth, double *sorted_vp);
 
+/* "Next" rows N1 + N2: one fixed-dimension MH move of one chain -- PROPOSAL (ENOS = 0 Cauchy step,
+ * prjmh_temper_rf.f90:1386-1447), INTERPLAYER_novar, CHECKBOUNDS2 (:1681-1716), LOGLHOOD and the
+ * accept test of EXPLORE_MH_NOVARPAR (:739-757).  Random numbers are inputs.  See the .c file. */
+int orc_mh_step(int k, double *node_depth, double *node_vp, double *logL,
+                int ivo, int iwhich, double cauchy, double u_acc, double beta, double sigma,
+                const double *prior,
+                const double *src_offset, const double *src_depth, int nsrc, const double *tobs,
+                double *prop_depth, double *prop_vp, double *logL_prop);
+void orc_mh_step_batch(const int *k, double *voro, double *logL, int B, int ldk,
+                       const int *ivo, const int *iwhich, const double *cauchy, const double *u_acc,
+                       const double *beta, const double *sigma, const double *prior,
+                       const double *src_offset, const double *src_depth, int nsrc,
+                       const double *tobs, int *accept, double *voro_prop, double *logL_prop);
+
 /* "Next" row N4: LOGLHOOD_RT's likelihood with the AR(1) residual model of IAR = 1
  * (loglhood.f90:171-182, ARPRED_RT :616-653, CHECKBOUNDS_ARMXRT :678-699). */
 double orc_loglhood_from_times_ar(const double *tpred, const double *tobs, int ndat, double sigma,

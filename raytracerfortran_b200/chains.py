@@ -1,0 +1,96 @@
+"""Fixed-dimension Metropolis-Hastings moves of many independent chains on the GPU (SURVEY 8f rows
+N1 + N2): the body of EXPLORE_MH_NOVARPAR's sweep (prjmh_temper_rf.f90:717-757) -- PROPOSAL
+(:1386-1447), INTERPLAYER_novar (loglhood.f90:214-295), CHECKBOUNDS2 (:1681-1716), LOGLHOOD and the
+accept test -- for B chains per launch through rtb200_mh_step_device (include/raytrace_b200.h).
+
+The reference runs one chain per MPI rank and one proposal at a time; batching ACROSS chains leaves
+every chain's Markov kernel unchanged.  Chain states live in HBM between moves: k [B] int32,
+voro [B, 2, ldk] float64 (row 0 node depths, row 1 vp, sorted by depth), logL [B], beta [B],
+sigma [B].  torch supplies the tensors, the stream and the random numbers; the move itself is the
+library's kernels.  Birth/death moves (BIRTH_FULL / DEATH_FULL) are not built.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .device import _ensure_device, _legacy_stream_handle, _ptr
+
+
+def prior_array(hmin=100.1, hmx=10000.1, vmin=1500.0, vmax=10000.0, pertsdsc=30.0, fact=1.0,
+                factor=1.0):
+    """The 7 doubles rtb200_mh_step_device takes as `prior`, from the parameter file's hmin / hmx
+    the way read_input.f90:207-214 derives them: minlim = (hmin, 1500), maxlim = (hmx, 10000),
+    pertsd = (maxlim - minlim)/pertsdsc (pertsdsc = 30, :169), step width fact/factor*pertsd
+    (fact = 1, rjmcmc_com.f90:80; factor = 1 in EXPLORE_MH_NOVARPAR's call, :735)."""
+    minlim = np.array([hmin, vmin], dtype=np.float64)
+    maxlim = np.array([hmx, vmax], dtype=np.float64)
+    pertsd = (maxlim - minlim) / np.float64(pertsdsc)
+    scale = np.float64(fact) / np.float64(factor) * pertsd
+    return np.array([scale[0], scale[1], minlim[0], minlim[1], maxlim[0], maxlim[1], hmin],
+                    dtype=np.float64)
+
+
+def cauchy_deviates(u):
+    """TAN(PI2*(ran_uni - 0.5)) of PROPOSAL (:1405; PI2 is pi, data_type.f90:5) for uniforms u."""
+    return torch.tan(math.pi * (u - 0.5))
+
+
+def mh_step_device(k, voro, logL, ivo, iwhich, cauchy, u_acc, beta, sigma, prior,
+                   src_offset, src_depth, tobs, accept=None, stream=None):
+    """One move of every chain, in place on `voro` and `logL`.
+
+    k [B] i32, voro [B, 2, ldk] f64, logL/beta/sigma/cauchy/u_acc [B] f64, ivo/iwhich [B] i32
+    (1-based node, 1 = depth / 2 = vp), src_offset/src_depth/tobs [NSrc] f64: CUDA tensors.
+    prior: 7 doubles on the host (prior_array).  Asynchronous on `stream` (default: torch's
+    current stream).  Returns accept [B] i32: 1 accepted, 0 rejected, -1 outside the bounds."""
+    if not voro.is_cuda:
+        raise ValueError("mh_step_device needs CUDA tensors (there is no CPU path)")
+    dev = voro.device
+    _ensure_device(dev.index if dev.index is not None else torch.cuda.current_device())
+    B, two, ldk = voro.shape
+    if two != 2:
+        raise ValueError("voro must be [B, 2, ldk]")
+    f64, i32 = torch.float64, torch.int32
+    if accept is None:
+        accept = torch.empty((B,), dtype=i32, device=dev)
+    pr = np.ascontiguousarray(prior, dtype=np.float64)
+    if pr.size != 7:
+        raise ValueError("prior must hold 7 doubles (see prior_array)")
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    import ctypes as C
+    rc = _lib.load().rtb200_mh_step_device(
+        _ptr(k, i32), _ptr(voro, f64), _ptr(logL, f64), B, ldk, _ptr(ivo, i32), _ptr(iwhich, i32),
+        _ptr(cauchy, f64), _ptr(u_acc, f64), _ptr(beta, f64), _ptr(sigma, f64),
+        pr.ctypes.data_as(C.POINTER(C.c_double)), _ptr(src_offset, f64), _ptr(src_depth, f64),
+        _ptr(tobs, f64), src_offset.numel(), _ptr(accept, i32),
+        st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle())
+    _lib.check(rc)
+    return accept
+
+
+def mh_sweep_device(k, voro, logL, beta, sigma, prior, src_offset, src_depth, tobs, generator=None,
+                    stats=None):
+    """EXPLORE_MH_NOVARPAR's sweep (:725-760) for every chain: for ivo = 1..max(k) and
+    iwhich = 1, 2 (skipping the fixed top node's depth, :730) propose, check, evaluate, accept.
+    Chains with fewer than ivo nodes sit the move out.  Uniforms come from `generator` (a CUDA
+    torch.Generator).  Returns (accepted, proposed) counts as device tensors [B]."""
+    dev = voro.device
+    B = voro.shape[0]
+    kmax = int(k.max().item())
+    acc_n = torch.zeros(B, dtype=torch.int64, device=dev)
+    prop_n = torch.zeros(B, dtype=torch.int64, device=dev)
+    accept = torch.empty(B, dtype=torch.int32, device=dev)
+    for ivo in range(1, kmax + 1):
+        iv = torch.full((B,), ivo, dtype=torch.int32, device=dev)
+        for iwhich in (1, 2):
+            if ivo == 1 and iwhich == 1:
+                continue
+            iw = torch.full((B,), iwhich, dtype=torch.int32, device=dev)
+            u = torch.rand((2, B), dtype=torch.float64, device=dev, generator=generator)
+            mh_step_device(k, voro, logL, iv, iw, cauchy_deviates(u[0]), u[1].contiguous(), beta,
+                           sigma, prior, src_offset, src_depth, tobs, accept=accept)
+            prop_n += (k >= ivo)
+            acc_n += (accept == 1)
+    return acc_n, prop_n

@@ -56,10 +56,25 @@ struct TileCfg {
     size_t smem;  // dynamic shared memory bytes
 };
 
+// Prior and proposal scales of the fixed-dimension MH move (read_input.f90:207-214).
+struct MhPrior {
+    double scale[2];    // fact/factor*pertsd(1:2)   Cauchy step widths: depth, vp
+    double minlim[2];   // minlim(1:2)
+    double maxlim[2];   // maxlim(1:2)
+    double hmin;        // minimum layer thickness
+};
+
 size_t      tile_smem_bytes(const TileCfg &c, int ldv, int ldz);
 cudaError_t launch_batch(const BatchArgs &a, const TileCfg &c, cudaStream_t st);
 cudaError_t launch_prep_voro(const int *k, const double *voro, int B, int ldk, double *vels,
                              double *depths, double *sorted, cudaStream_t st);
+cudaError_t launch_propose_voro(const int *k, const double *voro, int B, int ldk, const int *ivo,
+                                const int *iwhich, const double *cauchy, const MhPrior &pr,
+                                double *vels, double *depths, int *keval, double *prop,
+                                int *outside, cudaStream_t st);
+cudaError_t launch_mh_accept(const int *k, double *voro, const double *prop, double *logL,
+                             const double *logL_prop, const int *outside, const double *u_acc,
+                             const double *beta, int B, int ldk, int *accept, cudaStream_t st);
 int         max_ctas_per_sm(const TileCfg &c);   // occupancy of the batch kernel for this geometry
 cudaError_t fp64_peak(double *tflops, int repeats, cudaStream_t st);
 cudaError_t fastpath_selftest(double samples, unsigned long long seed, double *mismatches,

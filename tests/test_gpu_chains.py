@@ -1,0 +1,116 @@
+"""SURVEY 8f rows N1 + N2 on the GPU: rtb200_mh_step_device (PROPOSAL + INTERPLAYER_novar +
+CHECKBOUNDS2 + LOGLHOOD + accept, prjmh_temper_rf.f90:725-757) against the CPU oracle's
+restatement on the same random numbers."""
+import numpy as np
+import pytest
+
+import oracle
+from raytracerfortran_b200 import chains, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_chains(B, ldk, seed, hmin=100.1, hmx=10000.1):
+    rng = np.random.default_rng(seed)
+    k = rng.integers(1, ldk + 1, B).astype(np.int32)
+    voro = np.zeros((B, 2, ldk))
+    for b in range(B):
+        n = int(k[b])
+        # the top node at depth 0, the others at sorted depths at least hmin apart
+        gaps = hmin + rng.random(n - 1) * (hmx - hmin * n) / max(n, 1) if n > 1 else np.zeros(0)
+        voro[b, 0, 1:n] = np.cumsum(gaps)
+        voro[b, 1, :n] = rng.uniform(1500.0, 10000.0, n)
+    return k, voro
+
+
+def _setup(B, ldk, nsrc, seed):
+    k, voro = _random_chains(B, ldk, seed)
+    so, sd = workloads.make_sources(nsrc, seed)
+    tobs, sigma = workloads.make_observations(np.full(nsrc, 1.3), B, seed)
+    ll = np.array([oracle.loglhood_rt(voro[b, 1, :k[b]], voro[b, 0, 1:k[b]], so, sd, tobs, sigma[b])[0]
+                   for b in range(B)])
+    return k, voro, so, sd, tobs, sigma, ll
+
+
+def _dev(*arrays):
+    import torch
+    return [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrays]
+
+
+def test_mh_step_matches_oracle():
+    import torch
+    B, ldk, nsrc = 3000, 12, 24
+    k, voro, so, sd, tobs, sigma, ll = _setup(B, ldk, nsrc, 11)
+    rng = np.random.default_rng(12)
+    ivo = rng.integers(1, k + 2).astype(np.int32)            # includes ivo = k + 1 (no such node)
+    iwhich = rng.integers(1, 3, B).astype(np.int32)
+    u = rng.random((2, B))
+    cauchy = np.tan(np.pi * (u[0] - 0.5))
+    cauchy[::7] *= 0.01                                      # a good share of small, acceptable steps
+    beta = 1.0 / 1.4 ** rng.integers(0, 8, B)
+    prior = chains.prior_array()
+    want = oracle.mh_step_batch(k, voro, ll, ivo, iwhich, cauchy, u[1], beta, sigma, prior, so, sd, tobs)
+    tk, tv, tl, ti, tw, tc, tu, tb, tg, ts, td, to = _dev(k, voro, ll, ivo, iwhich, cauchy, u[1], beta,
+                                                          sigma, so, sd, tobs)
+    acc = chains.mh_step_device(tk, tv, tl, ti, tw, tc, tu, tb, tg, prior, ts, td, to)
+    torch.cuda.synchronize()
+    acc = acc.cpu().numpy()
+    assert np.array_equal(acc, want["accept"])
+    assert (acc == 1).sum() > 100 and (acc == 0).sum() > 100 and (acc == -1).sum() > 100
+    assert np.array_equal(tv.cpu().numpy().view(np.uint64), want["voro"].view(np.uint64))
+    got_ll = tl.cpu().numpy()
+    scale = np.maximum(np.abs(want["logL"]), nsrc * np.abs(np.log(sigma)))
+    assert np.all(np.abs(got_ll - want["logL"]) <= 1e-12 * scale)
+    assert np.array_equal(got_ll[acc != 1], ll[acc != 1])    # rejected chains keep their logL bits
+
+
+def test_mh_trajectory_matches_oracle():
+    """Forty moves in a row: the same decisions and bit-identical chain states at the end."""
+    import torch
+    B, ldk, nsrc = 512, 8, 20
+    k, voro, so, sd, tobs, sigma, ll = _setup(B, ldk, nsrc, 21)
+    rng = np.random.default_rng(22)
+    beta = 1.0 / 1.4 ** rng.integers(0, 4, B)
+    prior = chains.prior_array()
+    prior[:2] /= 10.0
+    tk, tv, tl, tb, tg, ts, td, to = _dev(k, voro, ll, beta, sigma, so, sd, tobs)
+    cur_v, cur_l = voro, ll
+    total = 0
+    for step in range(40):
+        ivo = (1 + step % ldk) * np.ones(B, dtype=np.int32)
+        iwhich = (1 + (step // ldk) % 2) * np.ones(B, dtype=np.int32)
+        u = rng.random((2, B))
+        cauchy = np.tan(np.pi * (u[0] - 0.5))
+        r = oracle.mh_step_batch(k, cur_v, cur_l, ivo, iwhich, cauchy, u[1], beta, sigma, prior, so, sd, tobs)
+        cur_v, cur_l = r["voro"], r["logL"]
+        ti, tw, tc, tu = _dev(ivo, iwhich, cauchy, u[1])
+        acc = chains.mh_step_device(tk, tv, tl, ti, tw, tc, tu, tb, tg, prior, ts, td, to)
+        assert np.array_equal(acc.cpu().numpy(), r["accept"]), f"step {step}"
+        total += int((r["accept"] == 1).sum())
+    assert total > 500
+    assert np.array_equal(tv.cpu().numpy().view(np.uint64), cur_v.view(np.uint64))
+
+
+def test_mh_sweep_device_runs_and_respects_the_prior():
+    import torch
+    B, ldk, nsrc = 2048, 10, 32
+    k, voro, so, sd, tobs, sigma, ll = _setup(B, ldk, nsrc, 31)
+    beta = np.ones(B)
+    prior = chains.prior_array()
+    tk, tv, tl, tb, tg, ts, td, to = _dev(k, voro, ll, beta, sigma, so, sd, tobs)
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    acc_n, prop_n = chains.mh_sweep_device(tk, tv, tl, tb, tg, prior, ts, td, to, generator=gen)
+    torch.cuda.synchronize()
+    assert int(prop_n.sum()) == int((2 * k - 1).sum())       # every node's vp, every node's depth but the top one
+    assert 0 < int(acc_n.sum()) < int(prop_n.sum())
+    v = tv.cpu().numpy()
+    for b in range(0, B, 37):
+        n = int(k[b])
+        z = v[b, 0, :n]
+        assert z[0] == 0.0 and np.all(np.diff(z) >= 100.1) and (n == 1 or z[-1] <= 10000.1)
+        assert np.all((v[b, 1, :n] >= 1500.0) & (v[b, 1, :n] <= 10000.0))
+    # the stored logL is the likelihood of the stored state
+    ref = np.array([oracle.loglhood_rt(v[b, 1, :k[b]], v[b, 0, 1:k[b]], so, sd, tobs, sigma[b])[0]
+                    for b in range(0, B, 37)])
+    got = tl.cpu().numpy()[::37]
+    assert np.all(np.abs(got - ref) <= 1e-12 * np.maximum(np.abs(ref), nsrc * np.abs(np.log(sigma[::37]))))
