@@ -94,3 +94,28 @@ def mh_sweep_device(k, voro, logL, beta, sigma, prior, src_offset, src_depth, to
             prop_n += (k >= ivo)
             acc_n += (accept == 1)
     return acc_n, prop_n
+
+
+def mh_moves_device(k, voro, logL, pos, n_moves, beta, sigma, prior, src_offset, src_depth, tobs,
+                    generator=None):
+    """n_moves launches in which EVERY chain makes its next move: chain b walks its own sweep
+    (ivo, iwhich) = (1,2), (2,1), (2,2), ..., (k_b,1), (k_b,2) -- EXPLORE_MH_NOVARPAR's order,
+    :725-731 -- and wraps around after its 2 k_b - 1 moves, so short chains do not idle while long
+    ones finish a lock-step sweep.  `pos` [B] i32 holds each chain's position in its sweep and is
+    advanced in place.  Returns the number of accepted moves per chain [B]."""
+    dev = voro.device
+    B = voro.shape[0]
+    period = (2 * k - 1).to(torch.int64)
+    # the whole schedule and all random numbers up front: the loop below is three launches a move
+    t = torch.arange(n_moves, device=dev, dtype=torch.int64)[:, None]
+    j = (pos.to(torch.int64)[None, :] + t) % period[None, :] + 1
+    ivo = (torch.div(j, 2, rounding_mode="floor") + 1).to(torch.int32).contiguous()
+    iwhich = (j % 2 + 1).to(torch.int32).contiguous()
+    u = torch.rand((2, n_moves, B), dtype=torch.float64, device=dev, generator=generator)
+    cauchy, u_acc = cauchy_deviates(u[0]).contiguous(), u[1].contiguous()
+    accept = torch.empty((n_moves, B), dtype=torch.int32, device=dev)
+    for m in range(n_moves):
+        mh_step_device(k, voro, logL, ivo[m], iwhich[m], cauchy[m], u_acc[m], beta, sigma, prior,
+                       src_offset, src_depth, tobs, accept=accept[m])
+    pos.copy_(((pos.to(torch.int64) + n_moves) % period).to(torch.int32))
+    return (accept == 1).sum(dim=0)

@@ -114,3 +114,34 @@ def test_mh_sweep_device_runs_and_respects_the_prior():
                     for b in range(0, B, 37)])
     got = tl.cpu().numpy()[::37]
     assert np.all(np.abs(got - ref) <= 1e-12 * np.maximum(np.abs(ref), nsrc * np.abs(np.log(sigma[::37]))))
+
+
+def test_mh_moves_device_walks_each_chains_own_sweep():
+    """mh_moves_device: chain b visits (1,2), (2,1), (2,2), ..., (k_b,2) and wraps; replayed on the
+    oracle with the same random numbers the chains end bit-identical."""
+    import math
+    import torch
+    B, ldk, nsrc, n_moves = 300, 6, 16, 9
+    k, voro, so, sd, tobs, sigma, ll = _setup(B, ldk, nsrc, 41)
+    beta = np.ones(B)
+    prior = chains.prior_array()
+    prior[:2] /= 10.0
+    tk, tv, tl, tb, tg, ts, td, to = _dev(k, voro, ll, beta, sigma, so, sd, tobs)
+    pos = torch.zeros(B, dtype=torch.int32, device="cuda")
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    nacc = chains.mh_moves_device(tk, tv, tl, pos, n_moves, tb, tg, prior, ts, td, to, generator=gen)
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    u = torch.rand((2, n_moves, B), dtype=torch.float64, device="cuda", generator=gen)
+    cauchy, uacc = torch.tan(math.pi * (u[0] - 0.5)).cpu().numpy(), u[1].cpu().numpy()
+    cur_v, cur_l, total = voro, ll, np.zeros(B, dtype=np.int64)
+    for m in range(n_moves):
+        j = m % (2 * k - 1) + 1                              # 1-based position in the chain's own sweep
+        ivo, iwhich = (j // 2 + 1).astype(np.int32), (j % 2 + 1).astype(np.int32)
+        assert np.all(ivo <= k) and not np.any((ivo == 1) & (iwhich == 1))
+        r = oracle.mh_step_batch(k, cur_v, cur_l, ivo, iwhich, cauchy[m], uacc[m], beta, sigma, prior,
+                                 so, sd, tobs)
+        cur_v, cur_l = r["voro"], r["logL"]
+        total += (r["accept"] == 1)
+    assert np.array_equal(nacc.cpu().numpy(), total)
+    assert np.array_equal(tv.cpu().numpy().view(np.uint64), cur_v.view(np.uint64))
+    assert np.array_equal(pos.cpu().numpy(), n_moves % (2 * k - 1))
