@@ -149,6 +149,25 @@ int rtb200_mh_step_device(const int *d_k, double *d_voro, double *d_logL, int B,
                           const double *d_src_depth, const double *d_tobs, int NSrc,
                           int *d_accept, void *stream);
 
+/* The birth/death move at the top of EXPLORE_MH_NOVARPAR (prjmh_temper_rf.f90:658-710) for B
+ * independent chains on the device: move choice from ran_unik (:666-680: 1/3 birth, 1/3 death,
+ * 1/3 neither; no birth at kmax, no death at kmin), BIRTH_FULL (:997-1103: new node at depth
+ * maxpert(1)*u_z with vp minlim(2)+maxpert(2)*u_v) or DEATH_FULL (:917-994: node idel of 2..k
+ * removed), INTERPLAYER_novar, CHECKBOUNDS (:1639-1678), LOGLHOOD, accept with
+ * logPr = LOG(pk(k'))-LOG(pk(k)) (Poisson prior on k, IPOIPR = 1, ENOS = 0).
+ *   d_k [B] in/out; d_voro [B][2][ldk] in/out (slots past k are zero); d_logL [B] in/out
+ *   d_uk, d_uz, d_uv, d_uacc [B]  uniforms: move choice, new depth, new vp, accept test
+ *   d_idel [B]                    node a death would remove (RANDPERM(k-1)(1)+1, in 2..k)
+ *   prior HOST [7] as for rtb200_mh_step_device; pk HOST [kmax] with pk[i-1] = pk(i)
+ *                                 (read_input.f90:78-81), or NULL for IPOIPR = 0
+ *   d_accept [B] out              1 accepted, 0 rejected, -1 outside the bounds, 2 no move proposed */
+int rtb200_bd_step_device(int *d_k, double *d_voro, double *d_logL, int B, int ldk,
+                          const double *d_uk, const int *d_idel, const double *d_uz,
+                          const double *d_uv, const double *d_uacc, const double *d_beta,
+                          const double *d_sigma, const double *prior, const double *pk, int kmin,
+                          int kmax, const double *d_src_offset, const double *d_src_depth,
+                          const double *d_tobs, int NSrc, int *d_accept, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Runtime control and introspection
  * ---------------------------------------------------------------------------------------- */

@@ -73,6 +73,9 @@ def lib():
         _lib.orc_mh_step_batch.restype = None
         _lib.orc_mh_step_batch.argtypes = [ip, dp, dp, C.c_int, C.c_int, ip, ip, dp, dp, dp, dp, dp,
                                            dp, dp, C.c_int, dp, ip, dp, dp]
+        _lib.orc_bd_step_batch.restype = None
+        _lib.orc_bd_step_batch.argtypes = [ip, dp, dp, C.c_int, C.c_int, dp, ip, dp, dp, dp, dp, dp, dp,
+                                           dp, C.c_int, C.c_int, dp, dp, C.c_int, dp, ip, ip, dp, dp]
         _lib.orc_batch_stats.restype = None
         _lib.orc_batch_stats.argtypes = [dp, dp, ip, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int,
                                          C.POINTER(Stats)]
@@ -146,6 +149,33 @@ def mh_step_batch(k, voro, logL, ivo, iwhich, cauchy, u_acc, beta, sigma, prior,
                             _p(_d(sigma)), _p(_d(prior)), _p(so), _p(sd), so.size, _p(ob),
                             acc.ctypes.data_as(I), _p(prop), _p(llp))
     return {"voro": vo, "logL": ll, "accept": acc, "voro_prop": prop, "logL_prop": llp}
+
+
+def bd_step_batch(k, voro, logL, u_k, idel, u_z, u_v, u_acc, beta, sigma, prior, pk, kmin, kmax,
+                  src_offset, src_depth, tobs):
+    """The birth/death move of B independent chains (orc_bd_step_batch).  Returns a dict with the
+    updated copies of k, voro, logL, `accept` [B] (1 / 0 / -1 outside / 2 no move), the proposals
+    (`k_prop`, `voro_prop`, `logL_prop`)."""
+    kk = np.array(k, dtype=np.int32, copy=True)
+    vo = np.array(voro, dtype=np.float64, order="C", copy=True)
+    ll = np.array(logL, dtype=np.float64, copy=True)
+    B, two, ldk = vo.shape
+    assert two == 2
+    so, sd, ob = _d(src_offset), _d(src_depth), _d(tobs)
+    acc = np.zeros(B, dtype=np.int32)
+    kp = kk.copy()
+    prop = vo.copy()
+    llp = np.full(B, np.nan)
+    I = C.POINTER(C.c_int)
+    idl = np.ascontiguousarray(idel, dtype=np.int32)
+    pkp = None if pk is None else _p(_d(pk))
+    lib().orc_bd_step_batch(kk.ctypes.data_as(I), _p(vo), _p(ll), B, ldk, _p(_d(u_k)),
+                            idl.ctypes.data_as(I), _p(_d(u_z)), _p(_d(u_v)), _p(_d(u_acc)),
+                            _p(_d(beta)), _p(_d(sigma)), _p(_d(prior)), pkp, int(kmin), int(kmax),
+                            _p(so), _p(sd), so.size, _p(ob), acc.ctypes.data_as(I),
+                            kp.ctypes.data_as(I), _p(prop), _p(llp))
+    return {"k": kk, "voro": vo, "logL": ll, "accept": acc, "k_prop": kp, "voro_prop": prop,
+            "logL_prop": llp}
 
 
 def loglhood_voro(node_depth, node_vp, src_offset, src_depth, tobs, sigma):

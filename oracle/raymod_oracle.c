@@ -568,6 +568,109 @@ int orc_mh_step(int k, double *node_depth, double *node_vp, double *logL,
     return ret;
 }
 
+/* ---- N2: the birth/death move at the top of EXPLORE_MH_NOVARPAR (:658-710) -------------- *
+ * Move choice from ran_unik (:666-680): at kmax only death, at kmin only birth, each with
+ * probability 0.3333; otherwise birth if <= 0.3333, death if > 0.6666.
+ * BIRTH_FULL (:997-1103): new node k+1 with depth maxpert(1)*u_z and vp minlim(2)+maxpert(2)*u_v
+ * (maxpert = maxlim - minlim, read_input.f90:213), INTERPLAYER_novar.
+ * DEATH_FULL (:917-994): node idel (2..k, the first element of RANDPERM(k-1) plus one) is zeroed,
+ * the k nodes are sorted, the first one is dropped (:957-960), INTERPLAYER_novar.
+ * logPr = LOG(pk(k_new)) - LOG(pk(k)) with the Poisson prior (IPOIPR = 1, ENOS = 0; :986,:1094),
+ * 0 when pk is NULL (IPOIPR = 0).  CHECKBOUNDS (:1639-1678), LOGLHOOD, accept test (:689-699).
+ * node_depth/node_vp have ldk slots; slots past k are zero and stay zero.
+ * Returns 1 accepted, 0 rejected, -1 outside the bounds, 2 no birth/death proposed.        */
+int orc_bd_step(int *k_io, double *node_depth, double *node_vp, double *logL, int ldk,
+                double u_k, int idel, double u_z, double u_v, double u_acc, double beta,
+                double sigma, const double *prior, const double *pk, int kmin, int kmax,
+                const double *src_offset, const double *src_depth, int nsrc, const double *tobs,
+                int *k_prop, double *prop_depth, double *prop_vp, double *logL_prop)
+{
+    const double minlim[2] = {prior[2], prior[3]}, maxlim[2] = {prior[4], prior[5]}, hmin = prior[6];
+    const int k = *k_io;
+    int i_bd = 0;
+    if (kmin != kmax) {                                          /* :661-680 */
+        if (k == kmax)      { if (u_k <= 0.3333) i_bd = 2; }
+        else if (k == kmin) { if (u_k <= 0.3333) i_bd = 1; }
+        else { if (u_k <= 0.3333) i_bd = 1; if (u_k > 0.6666) i_bd = 2; }
+    }
+    if (k_prop) *k_prop = k;
+    if (i_bd == 0) return 2;
+    if (k < 1 || k > ldk || (i_bd == 1 && k + 1 > ldk) || (i_bd == 2 && (k < 2 || idel < 2 || idel > k)))
+        return -1;
+    double *d = (double *)calloc((size_t)(2 * ldk + 2), sizeof(double));
+    double *v = d + ldk + 1;
+    memcpy(d, node_depth, sizeof(double) * (size_t)k);
+    memcpy(v, node_vp, sizeof(double) * (size_t)k);
+    int kn;
+    if (i_bd == 1) {
+        kn = k + 1;
+        d[k] = (maxlim[0] - minlim[0]) * u_z;                    /* :1035-1040 */
+        v[k] = minlim[1] + (maxlim[1] - minlim[1]) * u_v;        /* :1051 */
+        orc_interplayer_novar(kn, d, v);                         /* :1057 */
+    } else {
+        kn = k - 1;
+        d[idel - 1] = 0.0;                                       /* :948 */
+        v[idel - 1] = 0.0;
+        orc_interplayer_novar(k, d, v);                          /* :951-953 QSORTC2D over k nodes */
+        for (int i = 0; i < kn; ++i) { d[i] = d[i + 1]; v[i] = v[i + 1]; }   /* :957 */
+        d[kn] = 0.0; v[kn] = 0.0;                                /* :959 */
+        orc_interplayer_novar(kn, d, v);                         /* :962 */
+    }
+    const double logPr = pk ? log(pk[kn - 1]) - log(pk[k - 1]) : 0.0;       /* :986 / :1094 */
+    if (k_prop) *k_prop = kn;
+    if (prop_depth) memcpy(prop_depth, d, sizeof(double) * (size_t)ldk);
+    if (prop_vp) memcpy(prop_vp, v, sizeof(double) * (size_t)ldk);
+    int outside = 0;                                             /* CHECKBOUNDS :1650-1674 */
+    for (int ilay = 1; ilay <= kn - 1; ++ilay) {
+        const double zi = d[ilay];
+        const double hi = (ilay == 1) ? zi : zi - d[ilay - 1];
+        if (hmin > hi) outside = 1;
+        if (maxlim[0] < zi) outside = 1;
+    }
+    for (int ivo = 1; ivo <= kn; ++ivo) {
+        if (ivo > 1 && (d[ivo - 1] < 0.0 || d[ivo - 1] > maxlim[0])) outside = 1;
+        if ((v[ivo - 1] - minlim[1]) < 0.0 || (maxlim[1] - v[ivo - 1]) < 0.0) outside = 1;
+    }
+    int ret;
+    if (outside) {
+        ret = -1;                                                /* :700-704 */
+    } else {
+        const double ll = orc_loglhood_rt(kn, v, d + 1, src_offset, src_depth, nsrc, tobs, sigma, NULL);
+        if (logL_prop) *logL_prop = ll;
+        const double logPLratio = logPr + (ll - *logL) * beta;   /* :689-691 */
+        if (u_acc >= exp(logPLratio)) {
+            ret = 0;
+        } else {
+            memcpy(node_depth, d, sizeof(double) * (size_t)ldk);
+            memcpy(node_vp, v, sizeof(double) * (size_t)ldk);
+            *logL = ll;
+            *k_io = kn;
+            ret = 1;
+        }
+    }
+    free(d);
+    return ret;
+}
+
+void orc_bd_step_batch(int *k, double *voro, double *logL, int B, int ldk, const double *u_k,
+                       const int *idel, const double *u_z, const double *u_v, const double *u_acc,
+                       const double *beta, const double *sigma, const double *prior,
+                       const double *pk, int kmin, int kmax,
+                       const double *src_offset, const double *src_depth, int nsrc,
+                       const double *tobs, int *accept, int *k_prop, double *voro_prop,
+                       double *logL_prop)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int b = 0; b < B; ++b) {
+        double *row = voro + (size_t)b * 2 * ldk;
+        double *pr = voro_prop ? voro_prop + (size_t)b * 2 * ldk : NULL;
+        accept[b] = orc_bd_step(&k[b], row, row + ldk, &logL[b], ldk, u_k[b], idel[b], u_z[b], u_v[b],
+                                u_acc[b], beta[b], sigma[b], prior, pk, kmin, kmax, src_offset,
+                                src_depth, nsrc, tobs, k_prop ? &k_prop[b] : NULL, pr,
+                                pr ? pr + ldk : NULL, logL_prop ? &logL_prop[b] : NULL);
+    }
+}
+
 /* B independent chains, one move each; voro [B][2][ldk] (depth row, vp row), OpenMP over chains. */
 void orc_mh_step_batch(const int *k, double *voro, double *logL, int B, int ldk,
                        const int *ivo, const int *iwhich, const double *cauchy, const double *u_acc,

@@ -117,6 +117,22 @@ void orc_mh_step_batch(const int *k, double *voro, double *logL, int B, int ldk,
                        const double *src_offset, const double *src_depth, int nsrc,
                        const double *tobs, int *accept, double *voro_prop, double *logL_prop);
 
+/* N2: the birth/death move of EXPLORE_MH_NOVARPAR (:658-710): move choice, BIRTH_FULL (:997-1103) or
+ * DEATH_FULL (:917-994), CHECKBOUNDS (:1639-1678), LOGLHOOD, accept with the Poisson-prior logPr.
+ * Returns 1 accepted, 0 rejected, -1 outside, 2 no birth/death proposed.  See the .c file. */
+int orc_bd_step(int *k_io, double *node_depth, double *node_vp, double *logL, int ldk,
+                double u_k, int idel, double u_z, double u_v, double u_acc, double beta,
+                double sigma, const double *prior, const double *pk, int kmin, int kmax,
+                const double *src_offset, const double *src_depth, int nsrc, const double *tobs,
+                int *k_prop, double *prop_depth, double *prop_vp, double *logL_prop);
+void orc_bd_step_batch(int *k, double *voro, double *logL, int B, int ldk, const double *u_k,
+                       const int *idel, const double *u_z, const double *u_v, const double *u_acc,
+                       const double *beta, const double *sigma, const double *prior,
+                       const double *pk, int kmin, int kmax,
+                       const double *src_offset, const double *src_depth, int nsrc,
+                       const double *tobs, int *accept, int *k_prop, double *voro_prop,
+                       double *logL_prop);
+
 /* "Next" row N4: LOGLHOOD_RT's likelihood with the AR(1) residual model of IAR = 1
  * (loglhood.f90:171-182, ARPRED_RT :616-653, CHECKBOUNDS_ARMXRT :678-699). */
 double orc_loglhood_from_times_ar(const double *tpred, const double *tobs, int ndat, double sigma,

@@ -65,8 +65,15 @@ def main():
     pos = torch.zeros(B, dtype=torch.int32, device=dev)
     M = args.moves
 
+    pk = chains.poisson_pk(3.01, 1, ldk)
+
     def sweep(i):
         nonlocal beta
+        # the birth/death move that opens EXPLORE_MH_NOVARPAR (:658-710), then the fixed-k moves
+        u = torch.rand((5, B), dtype=torch.float64, device=dev, generator=gen)
+        idel = (2 + torch.floor(u[4] * (tk - 1).clamp(min=1))).to(torch.int32)
+        chains.bd_step_device(tk, tv, tl, u[0].contiguous(), idel, u[1].contiguous(), u[2].contiguous(),
+                              u[3].contiguous(), beta, tg, prior, pk, 1, ldk, ts, td, to)
         acc = chains.mh_moves_device(tk, tv, tl, pos, M, beta, tg, prior, ts, td, to, generator=gen)
         # swap round between replicas
         beta, _ = tempering.tempering_swap_round_device(tl, beta, seed=2026, round_index=i)
@@ -83,7 +90,7 @@ def main():
         acc_t = acc_t + sweep(1 + i).sum()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    moves = B * M * args.sweeps
+    moves = B * (M + 1) * args.sweeps
     tt = torch.tensor([wall, float(moves), float(acc_t.item())], dtype=torch.float64, device=dev)
     if world > 1:
         mx = tt.clone()
@@ -98,7 +105,7 @@ def main():
             "rounds": args.sweeps, "moves_per_round": M, "seconds": wall, "mh_moves": moves_all,
             "mh_moves_per_s": moves_all / wall, "evals_per_s": moves_all * nsrc / wall,
             "acceptance": acc_all / moves_all,
-            "kernel_launches_per_move": 3, "library_launches": rt.get_stat("launches") - launches0,
+            "kernel_launches_per_move": 3, "birth_death_moves_per_round": 1, "final_mean_k": float(tk.double().mean().item()), "library_launches": rt.get_stat("launches") - launches0,
             "max_k": int(k.max())}))
     if world > 1:
         dist.barrier()

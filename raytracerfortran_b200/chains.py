@@ -7,7 +7,8 @@ The reference runs one chain per MPI rank and one proposal at a time; batching A
 every chain's Markov kernel unchanged.  Chain states live in HBM between moves: k [B] int32,
 voro [B, 2, ldk] float64 (row 0 node depths, row 1 vp, sorted by depth), logL [B], beta [B],
 sigma [B].  torch supplies the tensors, the stream and the random numbers; the move itself is the
-library's kernels.  Birth/death moves (BIRTH_FULL / DEATH_FULL) are not built.
+library's kernels.  The birth/death move (BIRTH_FULL /
+DEATH_FULL, :658-710) is `bd_step_device`.
 """
 import math
 
@@ -65,6 +66,52 @@ def mh_step_device(k, voro, logL, ivo, iwhich, cauchy, u_acc, beta, sigma, prior
         _ptr(cauchy, f64), _ptr(u_acc, f64), _ptr(beta, f64), _ptr(sigma, f64),
         pr.ctypes.data_as(C.POINTER(C.c_double)), _ptr(src_offset, f64), _ptr(src_depth, f64),
         _ptr(tobs, f64), src_offset.numel(), _ptr(accept, i32),
+        st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle())
+    _lib.check(rc)
+    return accept
+
+
+def poisson_pk(lam, kmin, kmax):
+    """pk(ik) = EXP(-lambda)*lambda**ik/EXP(LOGFACTORIAL(ik)) for ik = kmin..kmax
+    (read_input.f90:78-81); returns an array of kmax doubles with pk[i-1] = pk(i)."""
+    pk = np.zeros(kmax, dtype=np.float64)
+    for ik in range(kmin, kmax + 1):
+        pk[ik - 1] = math.exp(-lam) * lam ** float(ik) / math.exp(math.lgamma(ik + 1.0))
+    return pk
+
+
+def bd_step_device(k, voro, logL, u_k, idel, u_z, u_v, u_acc, beta, sigma, prior, pk, kmin, kmax,
+                   src_offset, src_depth, tobs, accept=None, stream=None):
+    """The birth/death move of every chain (rtb200_bd_step_device), in place on k, voro, logL.
+    u_k/u_z/u_v/u_acc [B] f64 uniforms, idel [B] i32 (node a death removes, 2..k), pk: host array
+    (poisson_pk) or None.  Returns accept [B] i32: 1 / 0 / -1 outside / 2 no move proposed."""
+    if not voro.is_cuda:
+        raise ValueError("bd_step_device needs CUDA tensors (there is no CPU path)")
+    dev = voro.device
+    _ensure_device(dev.index if dev.index is not None else torch.cuda.current_device())
+    B, two, ldk = voro.shape
+    if two != 2:
+        raise ValueError("voro must be [B, 2, ldk]")
+    f64, i32 = torch.float64, torch.int32
+    if accept is None:
+        accept = torch.empty((B,), dtype=i32, device=dev)
+    pr = np.ascontiguousarray(prior, dtype=np.float64)
+    if pr.size != 7:
+        raise ValueError("prior must hold 7 doubles (see prior_array)")
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    pkp = None
+    if pk is not None:
+        pka = np.ascontiguousarray(pk, dtype=np.float64)
+        if pka.size < kmax:
+            raise ValueError("pk must hold kmax values")
+        pkp = pka.ctypes.data_as(dp)
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    rc = _lib.load().rtb200_bd_step_device(
+        _ptr(k, i32), _ptr(voro, f64), _ptr(logL, f64), B, ldk, _ptr(u_k, f64), _ptr(idel, i32),
+        _ptr(u_z, f64), _ptr(u_v, f64), _ptr(u_acc, f64), _ptr(beta, f64), _ptr(sigma, f64),
+        pr.ctypes.data_as(dp), pkp, int(kmin), int(kmax), _ptr(src_offset, f64),
+        _ptr(src_depth, f64), _ptr(tobs, f64), src_offset.numel(), _ptr(accept, i32),
         st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle())
     _lib.check(rc)
     return accept

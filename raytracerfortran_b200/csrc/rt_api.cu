@@ -55,7 +55,7 @@ struct Ctx {
     cudaEvent_t  ev_h2d[kMaxChunks], ev_k0[kMaxChunks], ev_k1[kMaxChunks];
     cudaEvent_t  ev_t0 = nullptr, ev_t1 = nullptr;
     DevBuf vels, depths, nl, off, dep, tobs, sigma, timeP, pout, logL, arena, voro, vsorted,
-        idxar, arparb, sched, mh_ll, mh_out;
+        idxar, arparb, sched, mh_ll, mh_out, mh_kp, mh_lpr;
     unsigned sched_seq = 0;        // launches take scheduler slots round robin
     bool     sched_dirty = false;  // a CUDA call failed: a kernel may have left counters behind
     void  *pin = nullptr;          // pinned staging for small calls
@@ -724,6 +724,69 @@ int rtb200_mh_step_device(const int *d_k, double *d_voro, double *d_logL, int B,
     return 0;
 }
 
+int rtb200_bd_step_device(int *d_k, double *d_voro, double *d_logL, int B, int ldk,
+                          const double *d_uk, const int *d_idel, const double *d_uz,
+                          const double *d_uv, const double *d_uacc, const double *d_beta,
+                          const double *d_sigma, const double *prior, const double *pk, int kmin,
+                          int kmax, const double *d_src_offset, const double *d_src_depth,
+                          const double *d_tobs, int NSrc, int *d_accept, void *stream) {
+    if (int rc = ensure_init()) return rc;
+    g.err.clear();
+    if (B <= 0) return 0;
+    if (NSrc <= 0) return fail("rtb200_bd_step_device needs at least one source");
+    if (ldk < 1 || ldk > 64) return fail("rtb200_bd_step_device supports 1..64 nodes per state");
+    if (!prior) return fail("rtb200_bd_step_device needs the prior array");
+    if (kmin < 1 || kmax < kmin || kmax > ldk) return fail("rtb200_bd_step_device needs 1 <= kmin <= kmax <= ldk");
+    cudaStream_t st = stream ? (cudaStream_t)stream : g.s_comp;
+    TileCfg cfg;
+    if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
+    const size_t Bz = (size_t)B, Bpad = (Bz + cfg.M - 1) / cfg.M * cfg.M + cfg.M;
+    CK(g.vels.reserve(Bpad * ldk * 8));
+    CK(g.depths.reserve(Bpad * ldk * 8));
+    CK(g.nl.reserve(Bpad * 4));
+    CK(g.vsorted.reserve(Bz * 2 * ldk * 8));
+    CK(g.mh_ll.reserve(Bz * 8));
+    CK(g.mh_out.reserve(Bz * 4));
+    CK(g.mh_kp.reserve(Bz * 4));
+    CK(g.mh_lpr.reserve(Bz * 8));
+    rtb::MhPrior pr;
+    pr.scale[0] = prior[0]; pr.scale[1] = prior[1];
+    pr.minlim[0] = prior[2]; pr.minlim[1] = prior[3];
+    pr.maxlim[0] = prior[4]; pr.maxlim[1] = prior[5];
+    pr.hmin = prior[6];
+    rtb::BdPrior bd{};
+    bd.kmin = kmin; bd.kmax = kmax; bd.use_pk = pk ? 1 : 0;
+    for (int i = kmin; pk && i <= kmax; ++i) bd.logpk[i - 1] = std::log(pk[i - 1]);   // LOG(pk(i)), libm
+    CK(rtb::launch_propose_bd(d_k, d_voro, B, ldk, d_uk, d_idel, d_uz, d_uv, pr, bd,
+                              g.vels.as<double>(), g.depths.as<double>(), g.nl.as<int>(),
+                              g.mh_kp.as<int>(), g.vsorted.as<double>(), g.mh_lpr.as<double>(),
+                              g.mh_out.as<int>(), st));
+    BatchArgs a{};
+    a.vels = g.vels.as<double>(); a.depths = g.depths.as<double>(); a.nlayers = g.nl.as<int>();
+    a.B = B; a.ldv = ldk; a.ldz = ldk; a.kmode = 1;
+    a.src_offset = d_src_offset; a.src_depth = d_src_depth;
+    a.tobs = d_tobs; a.nsrc = NSrc; a.sigma = d_sigma;
+    a.logL = g.mh_ll.as<double>();
+    a.logc = log_norm_const(NSrc);
+    a.padded = 1;
+    a.sched = next_sched();
+    CK(cudaEventRecord(g.ev_k0[0], st));
+    CK(rtb::launch_batch(a, cfg, st));
+    CK(cudaEventRecord(g.ev_k1[0], st));
+    CK(rtb::launch_bd_accept(d_k, d_voro, g.vsorted.as<double>(), g.mh_kp.as<int>(),
+                             g.mh_lpr.as<double>(), d_logL, g.mh_ll.as<double>(),
+                             g.mh_out.as<int>(), d_uacc, d_beta, B, ldk, d_accept, st));
+    g.launches += 3;
+    g.last = cfg;
+    if (!stream) {
+        CK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, g.ev_k0[0], g.ev_k1[0]));
+        g.kernel_ms = g.total_ms = ms;
+    }
+    return 0;
+}
+
 int rtb200_init(int device) { return ensure_init(device); }
 
 void rtb200_shutdown(void) {
@@ -735,7 +798,7 @@ void rtb200_shutdown(void) {
     g.pin_cap = 0;
     for (DevBuf *b : {&g.vels, &g.depths, &g.nl, &g.off, &g.dep, &g.tobs, &g.sigma,
                       &g.timeP, &g.pout, &g.logL, &g.arena, &g.voro, &g.vsorted, &g.idxar, &g.arparb,
-                      &g.sched, &g.mh_ll, &g.mh_out})
+                      &g.sched, &g.mh_ll, &g.mh_out, &g.mh_kp, &g.mh_lpr})
         b->release();
     for (int i = 0; i < kMaxChunks; ++i) {
         cudaEventDestroy(g.ev_h2d[i]);

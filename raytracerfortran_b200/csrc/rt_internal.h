@@ -64,6 +64,12 @@ struct MhPrior {
     double hmin;        // minimum layer thickness
 };
 
+// Birth/death move: range of k and the Poisson prior on k (read_input.f90:70-81) as LOG(pk(i)).
+struct BdPrior {
+    int    kmin, kmax, use_pk;
+    double logpk[64];   // logpk[i-1] = LOG(pk(i)), computed on the host
+};
+
 size_t      tile_smem_bytes(const TileCfg &c, int ldv, int ldz);
 cudaError_t launch_batch(const BatchArgs &a, const TileCfg &c, cudaStream_t st);
 cudaError_t launch_prep_voro(const int *k, const double *voro, int B, int ldk, double *vels,
@@ -75,6 +81,15 @@ cudaError_t launch_propose_voro(const int *k, const double *voro, int B, int ldk
 cudaError_t launch_mh_accept(const int *k, double *voro, const double *prop, double *logL,
                              const double *logL_prop, const int *outside, const double *u_acc,
                              const double *beta, int B, int ldk, int *accept, cudaStream_t st);
+cudaError_t launch_propose_bd(const int *k, const double *voro, int B, int ldk, const double *u_k,
+                              const int *idel, const double *u_z, const double *u_v,
+                              const MhPrior &pr, const BdPrior &bd, double *vels, double *depths,
+                              int *keval, int *kprop, double *prop, double *logpr, int *outside,
+                              cudaStream_t st);
+cudaError_t launch_bd_accept(int *k, double *voro, const double *prop, const int *kprop,
+                             const double *logpr, double *logL, const double *logL_prop,
+                             const int *outside, const double *u_acc, const double *beta, int B,
+                             int ldk, int *accept, cudaStream_t st);
 int         max_ctas_per_sm(const TileCfg &c);   // occupancy of the batch kernel for this geometry
 cudaError_t fp64_peak(double *tflops, int repeats, cudaStream_t st);
 cudaError_t fastpath_selftest(double samples, unsigned long long seed, double *mismatches,

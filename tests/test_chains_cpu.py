@@ -118,3 +118,56 @@ def test_chain_recovers_the_model(cfg1):
                 nprop += B
     assert np.all(ll > start) and 0.02 < nacc / nprop < 0.9
     assert np.all(np.diff(voro[:, 0, :k], axis=1) >= 100.1 - 1e-9)   # every state stayed inside the prior
+
+
+def test_poisson_pk_matches_read_input():
+    pk = chains.poisson_pk(3.01, 1, 10)
+    for ik in (1, 4, 10):                                        # read_input.f90:80
+        assert abs(pk[ik - 1] - math.exp(-3.01) * 3.01 ** ik / math.factorial(ik)) < 1e-15 * pk[ik - 1] * 10
+
+
+def test_birth_death_rules(cfg1):
+    """EXPLORE_MH_NOVARPAR :658-710 with BIRTH_FULL :997-1103 / DEATH_FULL :917-994."""
+    voro, k = cfg1["voro"], cfg1["k"]
+    so, sd, tobs = cfg1["so"], cfg1["sd"], cfg1["tobs"]
+    ll0 = np.array([oracle.loglhood_rt(voro[0, 1, :k], voro[0, 0, 1:k], so, sd, tobs, 0.02)[0]])
+    pr, pk = chains.prior_array(), chains.poisson_pk(3.01, 1, 10)
+    one = lambda x, dt=np.float64: np.array([x], dtype=dt)
+
+    def bd(u_k, idel=2, u_z=0.5, u_v=0.5, u_acc=0.0, kk=k, kmin=1, kmax=10, v=voro, pk_=pk):
+        return oracle.bd_step_batch(one(kk, np.int32), v, ll0, one(u_k), one(idel, np.int32), one(u_z),
+                                    one(u_v), one(u_acc), one(1.0), one(0.02), pr, pk_, kmin, kmax,
+                                    so, sd, tobs)
+    # move choice (:666-680)
+    assert bd(0.5)["accept"][0] == 2                             # middle third: stay
+    assert bd(0.2)["k_prop"][0] == k + 1 and bd(0.9)["k_prop"][0] == k - 1
+    assert bd(0.9, kmin=k)["accept"][0] == 2                     # at kmin no death ...
+    assert bd(0.2, kmin=k)["k_prop"][0] == k + 1                 # ... but birth with 1/3
+    assert bd(0.2, kmax=k)["k_prop"][0] == k - 1                 # at kmax "birth" third is death
+    assert bd(0.5, kmin=k, kmax=k)["accept"][0] == 2 and bd(0.1, kmin=k, kmax=k)["accept"][0] == 2
+    # birth: node at maxpert(1)*u_z with vp minlim(2)+maxpert(2)*u_v, sorted in (:1035-1057)
+    z_new, v_new = (10000.1 - 100.1) * 0.37, 1500.0 + (10000.0 - 1500.0) * 0.25
+    r = bd(0.2, u_z=0.37, u_v=0.25, u_acc=0.0)
+    zz = r["voro_prop"][0, 0, :k + 1]
+    assert np.all(np.diff(zz) > 0) and z_new in zz and r["voro_prop"][0, 1, list(zz).index(z_new)] == v_new
+    # u_acc = 0 accepts whatever the likelihood says unless outside; the state then holds k + 1 nodes
+    if r["accept"][0] == 1:
+        assert r["k"][0] == k + 1 and np.array_equal(r["voro"], r["voro_prop"])
+    # accept threshold includes the Poisson prior ratio (:986/:1094, :689-693)
+    thr = math.exp(math.log(pk[k]) - math.log(pk[k - 1]) + (r["logL_prop"][0] - ll0[0]) * 1.0)
+    for u in (thr * 0.999, thr * 1.001):
+        if 0 < u < 1:
+            assert bd(0.2, u_z=0.37, u_v=0.25, u_acc=u)["accept"][0] == (0 if u >= thr else 1)
+    # a birth closer than hmin to an interface is outside (:1650-1653)
+    u_close = (voro[0, 0, 2] + 50.0) / (10000.1 - 100.1)
+    assert bd(0.2, u_z=u_close)["accept"][0] == -1
+    # death of node idel: the remaining nodes keep their order, the slot past k - 1 is zero
+    r = bd(0.9, idel=3)
+    keep = [i for i in range(k) if i != 2]
+    assert r["k_prop"][0] == k - 1
+    assert np.array_equal(r["voro_prop"][0, :, :k - 1], voro[0][:, keep]) and np.all(r["voro_prop"][0, :, k - 1:] == 0)
+    thr = math.exp(math.log(pk[k - 2]) - math.log(pk[k - 1]) + (r["logL_prop"][0] - ll0[0]))
+    assert bd(0.9, idel=3, u_acc=min(thr * 1.001, 1.0))["accept"][0] == 0
+    # without the Poisson prior (IPOIPR = 0) logPr = 0
+    r0 = bd(0.9, idel=3, pk_=None)
+    assert r0["logL_prop"][0] == r["logL_prop"][0]

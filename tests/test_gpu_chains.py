@@ -145,3 +145,50 @@ def test_mh_moves_device_walks_each_chains_own_sweep():
     assert np.array_equal(nacc.cpu().numpy(), total)
     assert np.array_equal(tv.cpu().numpy().view(np.uint64), cur_v.view(np.uint64))
     assert np.array_equal(pos.cpu().numpy(), n_moves % (2 * k - 1))
+
+
+def test_bd_step_matches_oracle():
+    """rtb200_bd_step_device (birth/death, :658-710) against the oracle: same move choice, same
+    proposals, same decisions, bit-identical states; then a trajectory of mixed BD + MH moves."""
+    import torch
+    B, ldk, nsrc = 3000, 12, 24
+    kmin, kmax = 1, ldk
+    k, voro, so, sd, tobs, sigma, ll = _setup(B, ldk, nsrc, 51)
+    rng = np.random.default_rng(52)
+    prior, pk = chains.prior_array(), chains.poisson_pk(3.01, kmin, kmax)
+    beta = 1.0 / 1.4 ** rng.integers(0, 6, B)
+    tk, tv, tl, tb, tg, ts, td, to = _dev(k, voro, ll, beta, sigma, so, sd, tobs)
+    cur_k, cur_v, cur_l = k.copy(), voro, ll
+    seen = {1: 0, 0: 0, -1: 0, 2: 0}
+    for step in range(12):
+        u = rng.random((4, B))
+        idel = (2 + np.floor(rng.random(B) * np.maximum(cur_k - 1, 1))).astype(np.int32)
+        r = oracle.bd_step_batch(cur_k, cur_v, cur_l, u[0], idel, u[1], u[2], u[3], beta, sigma, prior,
+                                 pk, kmin, kmax, so, sd, tobs)
+        t_u = _dev(u[0], u[1], u[2], u[3])
+        (t_idel,) = _dev(idel)
+        acc = chains.bd_step_device(tk, tv, tl, t_u[0], t_idel, t_u[1], t_u[2], t_u[3], tb, tg, prior, pk,
+                                    kmin, kmax, ts, td, to)
+        acc = acc.cpu().numpy()
+        assert np.array_equal(acc, r["accept"]), f"step {step}"
+        assert np.array_equal(tk.cpu().numpy(), r["k"])
+        assert np.array_equal(tv.cpu().numpy().view(np.uint64), r["voro"].view(np.uint64)), f"step {step}"
+        cur_k, cur_v, cur_l = r["k"], r["voro"], r["logL"]
+        for c in seen:
+            seen[c] += int((acc == c).sum())
+        # interleave a fixed-dimension move so both kinds act on each other's states
+        ivo = np.minimum(1 + step % 4, cur_k).astype(np.int32)
+        iwhich = np.full(B, 2, dtype=np.int32)
+        uu = rng.random((2, B))
+        cauchy = 0.05 * np.tan(np.pi * (uu[0] - 0.5))
+        r2 = oracle.mh_step_batch(cur_k, cur_v, cur_l, ivo, iwhich, cauchy, uu[1], beta, sigma, prior, so, sd, tobs)
+        ti, tw, tc, tu = _dev(ivo, iwhich, cauchy, uu[1])
+        acc2 = chains.mh_step_device(tk, tv, tl, ti, tw, tc, tu, tb, tg, prior, ts, td, to)
+        assert np.array_equal(acc2.cpu().numpy(), r2["accept"]), f"mh step {step}"
+        cur_v, cur_l = r2["voro"], r2["logL"]
+    assert np.array_equal(tv.cpu().numpy().view(np.uint64), cur_v.view(np.uint64))
+    assert all(n > 50 for n in seen.values()), seen
+    got_ll = tl.cpu().numpy()
+    scale = np.maximum(np.abs(cur_l), nsrc * np.abs(np.log(sigma)))
+    assert np.all(np.abs(got_ll - cur_l) <= 1e-11 * scale)
+    assert cur_k.min() >= kmin and cur_k.max() <= kmax and len(np.unique(cur_k)) > 3

@@ -84,7 +84,7 @@ def _worker(rank, world, port, ret):
 
 def test_swap_round_world_size_2_gloo():
     world, port = 2, _free_port()
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()     # no fork() of a process that already runs OpenMP threads
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     h0, h1 = ret[0], ret[1]
