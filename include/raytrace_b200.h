@@ -168,6 +168,20 @@ int rtb200_bd_step_device(int *d_k, double *d_voro, double *d_logL, int B, int l
                           int kmax, const double *d_src_offset, const double *d_src_depth,
                           const double *d_tobs, int NSrc, int *d_accept, void *stream);
 
+/* The data-error move of EXPLORE_MH (prjmh_temper_rf.f90:545-575) for B independent chains on the
+ * device: chains whose gate uniform is >= 0.10 propose sdparRT + pertsdsdRT*gauss (PROPOSAL_SDRT,
+ * :1616-1635; outside unless within [minlimsdRT, maxlimsdRT]), the model is re-evaluated with the
+ * proposed sigma, and the move is rejected iff ran_uni >= EXP((logL_new - logL)*beta_mh).
+ *   d_voro [B][2][ldk], d_k [B] read only; d_logL [B], d_sigma [B] in/out
+ *   d_ugate, d_uacc [B] uniforms; d_gauss [B] standard normal deviates (GASDEVJ)
+ *   sd_prior HOST [3] = pertsdsdRT, minlimsdRT, maxlimsdRT          (read_input.f90:237-241)
+ *   d_accept [B] out: 1 accepted, 0 rejected, -1 outside the bounds, 2 no move proposed */
+int rtb200_sd_step_device(const int *d_k, const double *d_voro, double *d_logL, double *d_sigma,
+                          int B, int ldk, const double *d_ugate, const double *d_gauss,
+                          const double *d_uacc, const double *d_beta, const double *sd_prior,
+                          const double *d_src_offset, const double *d_src_depth,
+                          const double *d_tobs, int NSrc, int *d_accept, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Runtime control and introspection
  * ---------------------------------------------------------------------------------------- */

@@ -76,6 +76,9 @@ def lib():
         _lib.orc_bd_step_batch.restype = None
         _lib.orc_bd_step_batch.argtypes = [ip, dp, dp, C.c_int, C.c_int, dp, ip, dp, dp, dp, dp, dp, dp,
                                            dp, C.c_int, C.c_int, dp, dp, C.c_int, dp, ip, ip, dp, dp]
+        _lib.orc_sd_step_batch.restype = None
+        _lib.orc_sd_step_batch.argtypes = [ip, dp, dp, dp, C.c_int, C.c_int, dp, dp, dp, dp, dp,
+                                           dp, dp, C.c_int, dp, ip, dp]
         _lib.orc_batch_stats.restype = None
         _lib.orc_batch_stats.argtypes = [dp, dp, ip, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int,
                                          C.POINTER(Stats)]
@@ -176,6 +179,24 @@ def bd_step_batch(k, voro, logL, u_k, idel, u_z, u_v, u_acc, beta, sigma, prior,
                             kp.ctypes.data_as(I), _p(prop), _p(llp))
     return {"k": kk, "voro": vo, "logL": ll, "accept": acc, "k_prop": kp, "voro_prop": prop,
             "logL_prop": llp}
+
+
+def sd_step_batch(k, voro, logL, sigma, u_gate, gauss, u_acc, beta, sd_prior, src_offset, src_depth, tobs):
+    """The data-error move of B independent chains (orc_sd_step_batch).  Returns a dict with the
+    updated copies of logL and sigma, `accept` [B] (1 / 0 / -1 outside / 2 no move), `logL_prop`."""
+    kk = np.ascontiguousarray(k, dtype=np.int32)
+    vo = _d(voro)
+    ll = np.array(logL, dtype=np.float64, copy=True)
+    sg = np.array(sigma, dtype=np.float64, copy=True)
+    B, two, ldk = vo.shape
+    so, sd, ob = _d(src_offset), _d(src_depth), _d(tobs)
+    acc = np.zeros(B, dtype=np.int32)
+    llp = np.full(B, np.nan)
+    I = C.POINTER(C.c_int)
+    lib().orc_sd_step_batch(kk.ctypes.data_as(I), _p(vo), _p(ll), _p(sg), B, ldk, _p(_d(u_gate)),
+                            _p(_d(gauss)), _p(_d(u_acc)), _p(_d(beta)), _p(_d(sd_prior)), _p(so), _p(sd),
+                            so.size, _p(ob), acc.ctypes.data_as(I), _p(llp))
+    return {"logL": ll, "sigma": sg, "accept": acc, "logL_prop": llp}
 
 
 def loglhood_voro(node_depth, node_vp, src_offset, src_depth, tobs, sigma):

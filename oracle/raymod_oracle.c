@@ -671,6 +671,44 @@ void orc_bd_step_batch(int *k, double *voro, double *logL, int B, int ldk, const
     }
 }
 
+/* ---- the data-error move of EXPLORE_MH (:545-575): with probability 0.9 (ran_uni_ar >= 0.10)
+ * PROPOSAL_SDRT (:1616-1635: sdparRT + pertsdsdRT*gauss, outside unless within [minlimsdRT,
+ * maxlimsdRT]), LOGLHOOD (the travel times are recomputed: LOGLHOOD_RT ignores ipred), and
+ * "reject iff ran_uni >= EXP((logL_new - logL)*beta_mh)".  sd_prior = { pertsdsdRT, minlimsdRT,
+ * maxlimsdRT } (read_input.f90:237-241).  Returns 1 / 0 / -1 outside / 2 no move.            */
+int orc_sd_step(int k, const double *node_depth, const double *node_vp, double *logL, double *sigma,
+                double u_gate, double gauss, double u_acc, double beta, const double *sd_prior,
+                const double *src_offset, const double *src_depth, int nsrc, const double *tobs,
+                double *logL_prop)
+{
+    if (!(u_gate >= 0.10)) return 2;                             /* :553-554 */
+    const double snew = *sigma + sd_prior[0] * gauss;            /* :1630 */
+    if ((snew - sd_prior[1]) < 0.0 || (sd_prior[2] - snew) < 0.0) return -1;   /* :1631-1632, :569-573 */
+    const double ll = orc_loglhood_rt(k, node_vp, node_depth + 1, src_offset, src_depth, nsrc, tobs,
+                                      snew, NULL);
+    if (logL_prop) *logL_prop = ll;
+    const double logPLratio = (ll - *logL) * beta;               /* :560 */
+    if (u_acc >= exp(logPLratio)) return 0;                      /* :562-564 */
+    *sigma = snew;                                               /* :566 */
+    *logL = ll;
+    return 1;
+}
+
+void orc_sd_step_batch(const int *k, const double *voro, double *logL, double *sigma, int B, int ldk,
+                       const double *u_gate, const double *gauss, const double *u_acc,
+                       const double *beta, const double *sd_prior,
+                       const double *src_offset, const double *src_depth, int nsrc,
+                       const double *tobs, int *accept, double *logL_prop)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int b = 0; b < B; ++b) {
+        const double *row = voro + (size_t)b * 2 * ldk;
+        accept[b] = orc_sd_step(k[b], row, row + ldk, &logL[b], &sigma[b], u_gate[b], gauss[b],
+                                u_acc[b], beta[b], sd_prior, src_offset, src_depth, nsrc, tobs,
+                                logL_prop ? &logL_prop[b] : NULL);
+    }
+}
+
 /* B independent chains, one move each; voro [B][2][ldk] (depth row, vp row), OpenMP over chains. */
 void orc_mh_step_batch(const int *k, double *voro, double *logL, int B, int ldk,
                        const int *ivo, const int *iwhich, const double *cauchy, const double *u_acc,

@@ -133,6 +133,17 @@ void orc_bd_step_batch(int *k, double *voro, double *logL, int B, int ldk, const
                        const double *tobs, int *accept, int *k_prop, double *voro_prop,
                        double *logL_prop);
 
+/* N2: the data-error move of EXPLORE_MH (:545-575) with PROPOSAL_SDRT (:1616-1635). */
+int orc_sd_step(int k, const double *node_depth, const double *node_vp, double *logL, double *sigma,
+                double u_gate, double gauss, double u_acc, double beta, const double *sd_prior,
+                const double *src_offset, const double *src_depth, int nsrc, const double *tobs,
+                double *logL_prop);
+void orc_sd_step_batch(const int *k, const double *voro, double *logL, double *sigma, int B, int ldk,
+                       const double *u_gate, const double *gauss, const double *u_acc,
+                       const double *beta, const double *sd_prior,
+                       const double *src_offset, const double *src_depth, int nsrc,
+                       const double *tobs, int *accept, double *logL_prop);
+
 /* "Next" row N4: LOGLHOOD_RT's likelihood with the AR(1) residual model of IAR = 1
  * (loglhood.f90:171-182, ARPRED_RT :616-653, CHECKBOUNDS_ARMXRT :678-699). */
 double orc_loglhood_from_times_ar(const double *tpred, const double *tobs, int ndat, double sigma,

@@ -8,7 +8,7 @@ every chain's Markov kernel unchanged.  Chain states live in HBM between moves: 
 voro [B, 2, ldk] float64 (row 0 node depths, row 1 vp, sorted by depth), logL [B], beta [B],
 sigma [B].  torch supplies the tensors, the stream and the random numbers; the move itself is the
 library's kernels.  The birth/death move (BIRTH_FULL /
-DEATH_FULL, :658-710) is `bd_step_device`.
+DEATH_FULL, :658-710) is `bd_step_device`, the data-error move of EXPLORE_MH (:545-575) `sd_step_device`.
 """
 import math
 
@@ -117,6 +117,39 @@ def bd_step_device(k, voro, logL, u_k, idel, u_z, u_v, u_acc, beta, sigma, prior
     return accept
 
 
+def sd_prior_array(sdmn=0.001, sdmx=0.07, pertsdsdsc=10.0):
+    """pertsdsdRT, minlimsdRT, maxlimsdRT from the parameter file's sdmn / sdmx
+    (read_input.f90:237-241: pertsdsdRT = (sdmx - sdmn)/10)."""
+    return np.array([(np.float64(sdmx) - np.float64(sdmn)) / np.float64(pertsdsdsc), sdmn, sdmx],
+                    dtype=np.float64)
+
+
+def sd_step_device(k, voro, logL, sigma, u_gate, gauss, u_acc, beta, sd_prior, src_offset, src_depth,
+                   tobs, accept=None, stream=None):
+    """The data-error move of every chain (rtb200_sd_step_device), in place on sigma and logL.
+    Returns accept [B] i32: 1 / 0 / -1 outside / 2 no move proposed."""
+    if not voro.is_cuda:
+        raise ValueError("sd_step_device needs CUDA tensors (there is no CPU path)")
+    dev = voro.device
+    _ensure_device(dev.index if dev.index is not None else torch.cuda.current_device())
+    B, two, ldk = voro.shape
+    f64, i32 = torch.float64, torch.int32
+    if accept is None:
+        accept = torch.empty((B,), dtype=i32, device=dev)
+    sp = np.ascontiguousarray(sd_prior, dtype=np.float64)
+    if sp.size != 3:
+        raise ValueError("sd_prior must hold 3 doubles (see sd_prior_array)")
+    import ctypes as C
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    rc = _lib.load().rtb200_sd_step_device(
+        _ptr(k, i32), _ptr(voro, f64), _ptr(logL, f64), _ptr(sigma, f64), B, ldk, _ptr(u_gate, f64),
+        _ptr(gauss, f64), _ptr(u_acc, f64), _ptr(beta, f64), sp.ctypes.data_as(C.POINTER(C.c_double)),
+        _ptr(src_offset, f64), _ptr(src_depth, f64), _ptr(tobs, f64), src_offset.numel(),
+        _ptr(accept, i32), st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle())
+    _lib.check(rc)
+    return accept
+
+
 def mh_sweep_device(k, voro, logL, beta, sigma, prior, src_offset, src_depth, tobs, generator=None,
                     stats=None):
     """EXPLORE_MH_NOVARPAR's sweep (:725-760) for every chain: for ivo = 1..max(k) and
@@ -166,3 +199,42 @@ def mh_moves_device(k, voro, logL, pos, n_moves, beta, sigma, prior, src_offset,
                        src_offset, src_depth, tobs, accept=accept[m])
     pos.copy_(((pos.to(torch.int64) + n_moves) % period).to(torch.int32))
     return (accept == 1).sum(dim=0)
+
+
+def mcmc_step_device(k, voro, logL, sigma, beta, prior, sd_prior, pk, kmin, kmax, src_offset,
+                     src_depth, tobs, generator=None):
+    """One iteration of the sampler's worker loop (prjmh_temper_rf.f90:421-447) for every chain:
+    EXPLORE_MH_NOVARPAR -- the birth/death move, then the sweep over ivo = 1..k, iwhich = 1, 2 --
+    followed by EXPLORE_MH's data-error move.  All chains step together; a chain with fewer than
+    ivo nodes sits that move out, exactly as its own loop would have ended.  Everything stays on
+    the device; random numbers come from `generator`.  Returns a dict of per-chain counts
+    (device tensors): accepted / proposed fixed-k moves, birth/death and sigma outcomes."""
+    dev = voro.device
+    B, _, ldk = voro.shape
+    f64 = torch.float64
+    u = torch.rand((5, B), dtype=f64, device=dev, generator=generator)
+    idel = (2 + torch.floor(u[4] * (k - 1).clamp(min=1))).to(torch.int32)
+    bd = bd_step_device(k, voro, logL, u[0].contiguous(), idel, u[1].contiguous(), u[2].contiguous(),
+                        u[3].contiguous(), beta, sigma, prior, pk, kmin, kmax, src_offset, src_depth,
+                        tobs)
+    kmax_now = int(k.max().item())
+    n_moves = 2 * kmax_now - 1
+    uu = torch.rand((2, max(n_moves, 1), B), dtype=f64, device=dev, generator=generator)
+    cauchy, u_acc = cauchy_deviates(uu[0]).contiguous(), uu[1].contiguous()
+    accept = torch.empty((max(n_moves, 1), B), dtype=torch.int32, device=dev)
+    m = 0
+    for ivo in range(1, kmax_now + 1):
+        iv = torch.full((B,), ivo, dtype=torch.int32, device=dev)
+        for iwhich in (1, 2):
+            if ivo == 1 and iwhich == 1:
+                continue
+            iw = torch.full((B,), iwhich, dtype=torch.int32, device=dev)
+            mh_step_device(k, voro, logL, iv, iw, cauchy[m], u_acc[m], beta, sigma, prior, src_offset,
+                           src_depth, tobs, accept=accept[m])
+            m += 1
+    us = torch.rand((2, B), dtype=f64, device=dev, generator=generator)
+    gauss = torch.randn(B, dtype=f64, device=dev, generator=generator)
+    sd = sd_step_device(k, voro, logL, sigma, us[0].contiguous(), gauss, us[1].contiguous(), beta,
+                        sd_prior, src_offset, src_depth, tobs)
+    return {"accepted": (accept[:m] == 1).sum(dim=0), "proposed": 2 * k.to(torch.int64) - 1,
+            "bd": bd, "sd": sd}

@@ -787,6 +787,55 @@ int rtb200_bd_step_device(int *d_k, double *d_voro, double *d_logL, int B, int l
     return 0;
 }
 
+int rtb200_sd_step_device(const int *d_k, const double *d_voro, double *d_logL, double *d_sigma,
+                          int B, int ldk, const double *d_ugate, const double *d_gauss,
+                          const double *d_uacc, const double *d_beta, const double *sd_prior,
+                          const double *d_src_offset, const double *d_src_depth,
+                          const double *d_tobs, int NSrc, int *d_accept, void *stream) {
+    if (int rc = ensure_init()) return rc;
+    g.err.clear();
+    if (B <= 0) return 0;
+    if (NSrc <= 0) return fail("rtb200_sd_step_device needs at least one source");
+    if (ldk < 1 || ldk > 64) return fail("rtb200_sd_step_device supports 1..64 nodes per state");
+    if (!sd_prior) return fail("rtb200_sd_step_device needs the sd_prior array");
+    cudaStream_t st = stream ? (cudaStream_t)stream : g.s_comp;
+    TileCfg cfg;
+    if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
+    const size_t Bz = (size_t)B, Bpad = (Bz + cfg.M - 1) / cfg.M * cfg.M + cfg.M;
+    CK(g.vels.reserve(Bpad * ldk * 8));
+    CK(g.depths.reserve(Bpad * ldk * 8));
+    CK(g.nl.reserve(Bpad * 4));
+    CK(g.mh_ll.reserve(Bz * 8));
+    CK(g.mh_out.reserve(Bz * 4));
+    CK(g.mh_lpr.reserve(Bz * 8));
+    CK(rtb::launch_propose_sd(d_k, d_voro, B, ldk, d_sigma, d_ugate, d_gauss, sd_prior[0],
+                              sd_prior[1], sd_prior[2], g.vels.as<double>(), g.depths.as<double>(),
+                              g.nl.as<int>(), g.mh_lpr.as<double>(), g.mh_out.as<int>(), st));
+    BatchArgs a{};
+    a.vels = g.vels.as<double>(); a.depths = g.depths.as<double>(); a.nlayers = g.nl.as<int>();
+    a.B = B; a.ldv = ldk; a.ldz = ldk; a.kmode = 1;
+    a.src_offset = d_src_offset; a.src_depth = d_src_depth;
+    a.tobs = d_tobs; a.nsrc = NSrc; a.sigma = g.mh_lpr.as<double>();
+    a.logL = g.mh_ll.as<double>();
+    a.logc = log_norm_const(NSrc);
+    a.padded = 1;
+    a.sched = next_sched();
+    CK(cudaEventRecord(g.ev_k0[0], st));
+    CK(rtb::launch_batch(a, cfg, st));
+    CK(cudaEventRecord(g.ev_k1[0], st));
+    CK(rtb::launch_sd_accept(d_sigma, g.mh_lpr.as<double>(), d_logL, g.mh_ll.as<double>(),
+                             g.mh_out.as<int>(), d_uacc, d_beta, B, d_accept, st));
+    g.launches += 3;
+    g.last = cfg;
+    if (!stream) {
+        CK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, g.ev_k0[0], g.ev_k1[0]));
+        g.kernel_ms = g.total_ms = ms;
+    }
+    return 0;
+}
+
 int rtb200_init(int device) { return ensure_init(device); }
 
 void rtb200_shutdown(void) {

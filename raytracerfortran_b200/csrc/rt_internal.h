@@ -90,6 +90,13 @@ cudaError_t launch_bd_accept(int *k, double *voro, const double *prop, const int
                              const double *logpr, double *logL, const double *logL_prop,
                              const int *outside, const double *u_acc, const double *beta, int B,
                              int ldk, int *accept, cudaStream_t st);
+cudaError_t launch_propose_sd(const int *k, const double *voro, int B, int ldk, const double *sigma,
+                              const double *u_gate, const double *gauss, double pert, double smin,
+                              double smax, double *vels, double *depths, int *keval,
+                              double *sigma_prop, int *outside, cudaStream_t st);
+cudaError_t launch_sd_accept(double *sigma, const double *sigma_prop, double *logL,
+                             const double *logL_prop, const int *outside, const double *u_acc,
+                             const double *beta, int B, int *accept, cudaStream_t st);
 int         max_ctas_per_sm(const TileCfg &c);   // occupancy of the batch kernel for this geometry
 cudaError_t fp64_peak(double *tflops, int repeats, cudaStream_t st);
 cudaError_t fastpath_selftest(double samples, unsigned long long seed, double *mismatches,

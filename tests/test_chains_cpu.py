@@ -171,3 +171,26 @@ def test_birth_death_rules(cfg1):
     # without the Poisson prior (IPOIPR = 0) logPr = 0
     r0 = bd(0.9, idel=3, pk_=None)
     assert r0["logL_prop"][0] == r["logL_prop"][0]
+
+
+def test_sigma_move_rules(cfg1):
+    """EXPLORE_MH :545-575 with PROPOSAL_SDRT :1616-1635."""
+    voro, k = cfg1["voro"], cfg1["k"]
+    so, sd = cfg1["so"], cfg1["sd"]
+    tobs = cfg1["tobs"] + np.random.default_rng(3).normal(0, 0.016, len(so))
+    sp = chains.sd_prior_array()
+    assert sp.tolist() == [(0.07 - 0.001) / 10.0, 0.001, 0.07]
+    ll0 = np.array([oracle.loglhood_rt(voro[0, 1, :k], voro[0, 0, 1:k], so, sd, tobs, 0.05)[0]])
+    one = lambda x: np.array([x], dtype=np.float64)
+    step = lambda ug, g, ua, s=0.05: oracle.sd_step_batch([k], voro, ll0, one(s), one(ug), one(g), one(ua),
+                                                          one(1.0), sp, so, sd, tobs)
+    assert step(0.05, -1.0, 0.0)["accept"][0] == 2               # gate: no move 10 % of the time
+    r = step(0.5, -1.0, 0.0)                                     # sigma 0.05 -> 0.0431 fits noise 0.016 better
+    assert r["accept"][0] == 1 and r["sigma"][0] == 0.05 + sp[0] * -1.0 and r["logL"][0] > ll0[0]
+    assert r["logL"][0] == oracle.loglhood_rt(voro[0, 1, :k], voro[0, 0, 1:k], so, sd, tobs, r["sigma"][0])[0]
+    assert step(0.5, 5.0, 0.0)["accept"][0] == -1                # 0.0845 > sdmx
+    assert step(0.5, -8.0, 0.0)["accept"][0] == -1               # negative
+    r = step(0.5, 2.0, 0.0)                                      # a worse sigma: accepted only for small u
+    thr = math.exp(r["logL_prop"][0] - ll0[0])
+    assert 0 < thr < 1
+    assert step(0.5, 2.0, thr * 1.001)["accept"][0] == 0 and step(0.5, 2.0, thr * 0.999)["accept"][0] == 1

@@ -192,3 +192,71 @@ def test_bd_step_matches_oracle():
     scale = np.maximum(np.abs(cur_l), nsrc * np.abs(np.log(sigma)))
     assert np.all(np.abs(got_ll - cur_l) <= 1e-11 * scale)
     assert cur_k.min() >= kmin and cur_k.max() <= kmax and len(np.unique(cur_k)) > 3
+
+
+def test_sd_step_matches_oracle():
+    """rtb200_sd_step_device (the data-error move, :545-575) against the oracle, ten moves in a row."""
+    import torch
+    B, ldk, nsrc = 2000, 10, 24
+    k, voro, so, sd, tobs, sigma, ll = _setup(B, ldk, nsrc, 61)
+    rng = np.random.default_rng(62)
+    sp = chains.sd_prior_array()
+    beta = 1.0 / 1.4 ** rng.integers(0, 6, B)
+    tk, tv, tl, tb, tg, ts, td, to = _dev(k, voro, ll, beta, sigma, so, sd, tobs)
+    cur_l, cur_s = ll, sigma
+    seen = {1: 0, 0: 0, -1: 0, 2: 0}
+    for step in range(10):
+        u = rng.random((2, B))
+        gauss = rng.standard_normal(B)
+        r = oracle.sd_step_batch(k, voro, cur_l, cur_s, u[0], gauss, u[1], beta, sp, so, sd, tobs)
+        tu0, tga, tu1 = _dev(u[0], gauss, u[1])
+        acc = chains.sd_step_device(tk, tv, tl, tg, tu0, tga, tu1, tb, sp, ts, td, to).cpu().numpy()
+        assert np.array_equal(acc, r["accept"]), f"step {step}"
+        assert np.array_equal(tg.cpu().numpy().view(np.uint64), r["sigma"].view(np.uint64))
+        cur_l, cur_s = r["logL"], r["sigma"]
+        for c in seen:
+            seen[c] += int((acc == c).sum())
+    assert all(n > 50 for n in seen.values()), seen
+    got = tl.cpu().numpy()
+    assert np.all(np.abs(got - cur_l) <= 1e-11 * np.maximum(np.abs(cur_l), nsrc * np.abs(np.log(cur_s))))
+    assert np.array_equal(tv.cpu().numpy(), voro)                # the model is untouched
+
+
+def test_mcmc_step_device_samples_a_sane_posterior():
+    """The whole worker-loop iteration (birth/death + sweep + sigma move) on chains started at the
+    test_1 model with its noisy data: chains stay inside the prior, the stored logL is the
+    likelihood of the stored state, sigma drifts towards the noise level, k spreads out."""
+    import json, os, torch
+    c = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.json")))["config1"]
+    so, sd = np.array(c["src_offset_full"]), np.array(c["src_depth_full"])
+    v, z = np.array(c["vels"]), np.array(c["depths"])
+    t, _, _ = oracle.trace_rays(v, z, so, sd)
+    rng = np.random.default_rng(71)
+    tobs = t + rng.normal(0, 0.016, len(so))
+    B, ldk, k0 = 256, 10, len(v)
+    voro = np.zeros((B, 2, ldk))
+    voro[:, 0, 1:k0] = z
+    voro[:, 1, :k0] = v
+    k = np.full(B, k0, dtype=np.int32)
+    sigma = np.full(B, 0.05)
+    ll = np.full(B, oracle.loglhood_rt(v, z, so, sd, tobs, 0.05)[0])
+    beta = np.ones(B)
+    tk, tv, tl, tg, tb, ts, td, to = _dev(k, voro, ll, sigma, beta, so, sd, tobs)
+    prior, sp, pk = chains.prior_array(), chains.sd_prior_array(), chains.poisson_pk(3.01, 1, ldk)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    acc = prop = 0
+    for it in range(30):
+        r = chains.mcmc_step_device(tk, tv, tl, tg, tb, prior, sp, pk, 1, ldk, ts, td, to, generator=gen)
+        acc, prop = acc + int(r["accepted"].sum()), prop + int(r["proposed"].sum())
+    kk, vv, sg, got = tk.cpu().numpy(), tv.cpu().numpy(), tg.cpu().numpy(), tl.cpu().numpy()
+    assert 0.01 < acc / prop < 0.9
+    assert kk.min() >= 1 and kk.max() <= ldk and len(np.unique(kk)) >= 2
+    assert np.all((sg >= 0.001) & (sg <= 0.07)) and np.median(sg) < 0.05
+    for b in range(0, B, 9):
+        n = int(kk[b])
+        zz = vv[b, 0, :n]
+        assert zz[0] == 0.0 and np.all(np.diff(zz) >= 100.1) and np.all(vv[b, :, n:] == 0)
+        assert np.all((vv[b, 1, :n] >= 1500.0) & (vv[b, 1, :n] <= 10000.0))
+        ref = oracle.loglhood_rt(vv[b, 1, :n], zz[1:], so, sd, tobs, sg[b])[0]
+        assert abs(got[b] - ref) <= 1e-11 * max(abs(ref), 20 * abs(np.log(sg[b])))
+    assert np.median(got) > ll[0]                                 # the chains moved to better-fitting states
