@@ -260,3 +260,48 @@ def test_mcmc_step_device_samples_a_sane_posterior():
         ref = oracle.loglhood_rt(vv[b, 1, :n], zz[1:], so, sd, tobs, sg[b])[0]
         assert abs(got[b] - ref) <= 1e-11 * max(abs(ref), 20 * abs(np.log(sg[b])))
     assert np.median(got) > ll[0]                                 # the chains moved to better-fitting states
+
+
+def test_chain_moves_survive_hostile_inputs():
+    """Garbage in some chains (NaN / Inf deviates, node counts and indices out of range, NaN
+    states) must neither hang nor disturb the other chains, which still match the oracle."""
+    import torch
+    B, ldk, nsrc = 1024, 8, 16
+    k, voro, so, sd, tobs, sigma, ll = _setup(B, ldk, nsrc, 81)
+    rng = np.random.default_rng(82)
+    ivo = rng.integers(1, k + 1).astype(np.int32)
+    iwhich = rng.integers(1, 3, B).astype(np.int32)
+    u = rng.random((2, B))
+    cauchy = 0.1 * np.tan(np.pi * (u[0] - 0.5))
+    beta = np.ones(B)
+    prior = chains.prior_array()
+    want = oracle.mh_step_batch(k, voro, ll, ivo, iwhich, cauchy, u[1], beta, sigma, prior, so, sd, tobs)
+    bad = np.arange(B) % 4 == 0
+    kb, vb, ib, wb, cb, ub, lb = k.copy(), voro.copy(), ivo.copy(), iwhich.copy(), cauchy.copy(), u[1].copy(), ll.copy()
+    sel = np.flatnonzero(bad)
+    kb[sel[0::6]] = 0
+    kb[sel[1::6]] = ldk + 5
+    ib[sel[2::6]] = -3
+    wb[sel[2::6]] = 7
+    cb[sel[3::6]] = np.inf
+    cb[sel[4::6]] = np.nan
+    vb[sel[5::6], 0, 1] = np.nan
+    ub[sel[3::6]] = np.nan
+    tk, tv, tl, ti, tw, tc, tu, tb, tg, ts, td, to = _dev(kb, vb, lb, ib, wb, cb, ub, beta, sigma, so, sd, tobs)
+    acc = chains.mh_step_device(tk, tv, tl, ti, tw, tc, tu, tb, tg, prior, ts, td, to)
+    torch.cuda.synchronize()
+    acc = acc.cpu().numpy()
+    assert set(np.unique(acc)) <= {-1, 0, 1}
+    good = ~bad
+    assert np.array_equal(acc[good], want["accept"][good])
+    assert np.array_equal(tv.cpu().numpy()[good].view(np.uint64), want["voro"][good].view(np.uint64))
+    # the birth/death and sigma moves on the same garbage: they must come back
+    pk = chains.poisson_pk(3.01, 1, ldk)
+    uu = _dev(rng.random(B), rng.random(B), rng.random(B), ub)
+    (idel,) = _dev(rng.integers(-2, ldk + 3, B).astype(np.int32))
+    a2 = chains.bd_step_device(tk, tv, tl, uu[0], idel, uu[1], uu[2], uu[3], tb, tg, prior, pk, 1, ldk, ts, td, to)
+    a3 = chains.sd_step_device(tk, tv, tl, tg, uu[0], tc, uu[3], tb, chains.sd_prior_array(), ts, td, to)
+    torch.cuda.synchronize()
+    assert set(np.unique(a2.cpu().numpy())) <= {-1, 0, 1, 2} and set(np.unique(a3.cpu().numpy())) <= {-1, 0, 1, 2}
+    kk = tk.cpu().numpy()
+    assert np.all((kk[good] >= 1) & (kk[good] <= ldk))
