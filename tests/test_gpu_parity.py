@@ -227,6 +227,25 @@ def test_tile_scheduling_and_host_pipeline_options(variant):
     assert rt.get_stat("grid") < B // 8          # the tiles did outnumber the CTAs
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_more_models_per_tile_than_threads(variant):
+    """Few sources and shallow models let a tile hold more models than the CTA has threads."""
+    rt.set_option("variant", variant)
+    B, nsrc = 5000, 3
+    v, z, nl = workloads.make_models(B, 2, 91)
+    so, sd = workloads.make_sources(nsrc, 91)
+    tobs, sigma = workloads.make_observations(np.ones(nsrc), B, 91)
+    ref = oracle.dff_batch(v, z, nl, so, sd, tobs=tobs, sigma=sigma)
+    for opts in ({}, {"threads": 64, "tile_models": 300}, {"threads": 128, "ctas_per_sm": 1, "tile_models": 600}):
+        for k_, v_ in opts.items():
+            rt.set_option(k_, v_)
+        got = rt.dff_batch(v, z, nl, so, sd, tobs=tobs, sigma=sigma)
+        assert_bitexact(got["timeP"], ref["timeP"], f"timeP {opts}")
+        assert_logl_close(got["logL"], ref["logL"], nsrc, sigma)
+        if opts:
+            assert rt.get_stat("tile_models") > rt.get_stat("threads")
+
+
 def test_empty_and_single():
     v, z, nl = workloads.make_models(1, 6, 1)
     so, sd = workloads.make_sources(1, 1)
