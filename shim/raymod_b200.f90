@@ -17,7 +17,7 @@ module raymod
    use, intrinsic :: iso_c_binding, only : c_double, c_int
    implicit none
    private
-   public :: TraceRays, dofullforwardproblem, dff_batch, loglhood_batch
+   public :: TraceRays, dofullforwardproblem, dff_batch, loglhood_batch, loglhood_batch_ar, loglhood_batch_voro
 
    interface
       ! void tracerays_(vels, depths, NLayers, src_offset, src_depth, NSrc, timeP, keep_delta)
@@ -51,6 +51,31 @@ module raymod
          real(c_double), intent(out) :: logL(*), tpred(*)
          integer(c_int) :: status
       end function loglhood_batch
+
+      ! int loglhood_batch_ar(k, vp, ziface, B, ldv, ldz, src_offset, src_depth, NSrc, tobs, sigma,
+      !                       idxar, arpar, armx, logL, tpred)      -- IAR = 1 (loglhood.f90:171-182)
+      function loglhood_batch_ar(k, vp, ziface, B, ldv, ldz, src_offset, src_depth, NSrc, &
+                                 tobs, sigma, idxar, arpar, armx, logL, tpred) &
+            bind(C, name="loglhood_batch_ar") result(status)
+         import :: c_double, c_int
+         integer(c_int), intent(in)  :: k(*), B, ldv, ldz, NSrc, idxar(*)
+         real(c_double), intent(in)  :: vp(*), ziface(*), src_offset(*), src_depth(*), tobs(*), sigma(*)
+         real(c_double), intent(in)  :: arpar(*), armx
+         real(c_double), intent(out) :: logL(*), tpred(*)
+         integer(c_int) :: status
+      end function loglhood_batch_ar
+
+      ! int loglhood_batch_voro(k, voro, B, ldk, src_offset, src_depth, NSrc, tobs, sigma, logL,
+      !                         tpred, voro_sorted)   -- INTERPLAYER_novar + LOGLHOOD on voro(ldk,2,B)
+      function loglhood_batch_voro(k, voro, B, ldk, src_offset, src_depth, NSrc, tobs, sigma, &
+                                   logL, tpred, voro_sorted) &
+            bind(C, name="loglhood_batch_voro") result(status)
+         import :: c_double, c_int
+         integer(c_int), intent(in)  :: k(*), B, ldk, NSrc
+         real(c_double), intent(in)  :: voro(*), src_offset(*), src_depth(*), tobs(*), sigma(*)
+         real(c_double), intent(out) :: logL(*), tpred(*), voro_sorted(*)
+         integer(c_int) :: status
+      end function loglhood_batch_voro
    end interface
 
 contains
