@@ -104,3 +104,13 @@ def test_product_never_touches_the_oracle():
     assert not offenders, offenders
     out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_fortran_shim_binds_only_exported_symbols():
+    """shim/raymod_b200.f90 cannot be compiled here (no Fortran compiler); at least every C name it
+    binds must be one the library exports and the header declares."""
+    import re
+    src = open(os.path.join(ROOT, "shim", "raymod_b200.f90")).read()
+    names = set(re.findall(r'bind\(C,\s*name="([A-Za-z0-9_]+)"\)', src))
+    assert {"tracerays_", "dff_batch", "loglhood_batch"} <= names
+    assert names <= set(_lib.EXPORTS), names - set(_lib.EXPORTS)
