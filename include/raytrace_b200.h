@@ -149,6 +149,18 @@ int rtb200_mh_step_device(const int *d_k, double *d_voro, double *d_logL, int B,
                           const double *d_src_depth, const double *d_tobs, int NSrc,
                           int *d_accept, void *stream);
 
+/* n_moves consecutive calls of rtb200_mh_step_device in one: move m uses row m of d_ivo, d_iwhich,
+ * d_cauchy, d_uacc and writes row m of d_accept (all [n_moves][B]).  The run is captured once into
+ * a CUDA graph and replayed for as long as the caller passes the same buffers and sizes (refill
+ * them in place), which removes the launch gaps between the three kernels of every move.
+ * n_moves <= 512. */
+int rtb200_mh_moves_device(const int *d_k, double *d_voro, double *d_logL, int B, int ldk,
+                           int n_moves, const int *d_ivo, const int *d_iwhich,
+                           const double *d_cauchy, const double *d_uacc, const double *d_beta,
+                           const double *d_sigma, const double *prior, const double *d_src_offset,
+                           const double *d_src_depth, const double *d_tobs, int NSrc,
+                           int *d_accept, void *stream);
+
 /* The birth/death move at the top of EXPLORE_MH_NOVARPAR (prjmh_temper_rf.f90:658-710) for B
  * independent chains on the device: move choice from ran_unik (:666-680: 1/3 birth, 1/3 death,
  * 1/3 neither; no birth at kmax, no death at kmin), BIRTH_FULL (:997-1103: new node at depth

@@ -68,7 +68,6 @@ def main():
     pk = chains.poisson_pk(3.01, 1, ldk)
 
     def sweep(i):
-        nonlocal beta
         # the birth/death move that opens EXPLORE_MH_NOVARPAR (:658-710), then the fixed-k moves
         u = torch.rand((5, B), dtype=torch.float64, device=dev, generator=gen)
         idel = (2 + torch.floor(u[4] * (tk - 1).clamp(min=1))).to(torch.int32)
@@ -76,7 +75,8 @@ def main():
                               u[3].contiguous(), beta, tg, prior, pk, 1, ldk, ts, td, to)
         acc = chains.mh_moves_device(tk, tv, tl, pos, M, beta, tg, prior, ts, td, to, generator=gen)
         # swap round between replicas
-        beta, _ = tempering.tempering_swap_round_device(tl, beta, seed=2026, round_index=i)
+        nb, _ = tempering.tempering_swap_round_device(tl, beta, seed=2026, round_index=i)
+        beta.copy_(nb)          # same buffer every round: the captured graph of moves stays valid
         return acc
 
     sweep(0)

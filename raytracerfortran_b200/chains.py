@@ -176,29 +176,53 @@ def mh_sweep_device(k, voro, logL, beta, sigma, prior, src_offset, src_depth, to
     return acc_n, prop_n
 
 
+_moves_buffers = {}
+
+
 def mh_moves_device(k, voro, logL, pos, n_moves, beta, sigma, prior, src_offset, src_depth, tobs,
                     generator=None):
-    """n_moves launches in which EVERY chain makes its next move: chain b walks its own sweep
+    """n_moves moves in which EVERY chain makes its next move: chain b walks its own sweep
     (ivo, iwhich) = (1,2), (2,1), (2,2), ..., (k_b,1), (k_b,2) -- EXPLORE_MH_NOVARPAR's order,
     :725-731 -- and wraps around after its 2 k_b - 1 moves, so short chains do not idle while long
     ones finish a lock-step sweep.  `pos` [B] i32 holds each chain's position in its sweep and is
-    advanced in place.  Returns the number of accepted moves per chain [B]."""
+    advanced in place.  The schedule and all random numbers are generated up front into buffers
+    that persist between calls, and the run of moves goes to rtb200_mh_moves_device, which replays
+    it as one CUDA graph.  Returns the number of accepted moves per chain [B]."""
     dev = voro.device
-    B = voro.shape[0]
+    _ensure_device(dev.index if dev.index is not None else torch.cuda.current_device())
+    B, two, ldk = voro.shape
+    f64, i32 = torch.float64, torch.int32
+    key = (dev, B, int(n_moves))
+    buf = _moves_buffers.get(key)
+    if buf is None:
+        buf = {"ivo": torch.empty((n_moves, B), dtype=i32, device=dev),
+               "iwhich": torch.empty((n_moves, B), dtype=i32, device=dev),
+               "u": torch.empty((2, n_moves, B), dtype=f64, device=dev),
+               "cauchy": torch.empty((n_moves, B), dtype=f64, device=dev),
+               "accept": torch.empty((n_moves, B), dtype=i32, device=dev)}
+        _moves_buffers.clear()                      # one shape at a time: the library caches one graph
+        _moves_buffers[key] = buf
     period = (2 * k - 1).to(torch.int64)
-    # the whole schedule and all random numbers up front: the loop below is three launches a move
     t = torch.arange(n_moves, device=dev, dtype=torch.int64)[:, None]
     j = (pos.to(torch.int64)[None, :] + t) % period[None, :] + 1
-    ivo = (torch.div(j, 2, rounding_mode="floor") + 1).to(torch.int32).contiguous()
-    iwhich = (j % 2 + 1).to(torch.int32).contiguous()
-    u = torch.rand((2, n_moves, B), dtype=torch.float64, device=dev, generator=generator)
-    cauchy, u_acc = cauchy_deviates(u[0]).contiguous(), u[1].contiguous()
-    accept = torch.empty((n_moves, B), dtype=torch.int32, device=dev)
-    for m in range(n_moves):
-        mh_step_device(k, voro, logL, ivo[m], iwhich[m], cauchy[m], u_acc[m], beta, sigma, prior,
-                       src_offset, src_depth, tobs, accept=accept[m])
-    pos.copy_(((pos.to(torch.int64) + n_moves) % period).to(torch.int32))
-    return (accept == 1).sum(dim=0)
+    buf["ivo"].copy_(torch.div(j, 2, rounding_mode="floor") + 1)
+    buf["iwhich"].copy_(j % 2 + 1)
+    buf["u"].uniform_(generator=generator)
+    torch.tan(math.pi * (buf["u"][0] - 0.5), out=buf["cauchy"])
+    pr = np.ascontiguousarray(prior, dtype=np.float64)
+    if pr.size != 7:
+        raise ValueError("prior must hold 7 doubles (see prior_array)")
+    import ctypes as C
+    st = torch.cuda.current_stream(dev)
+    rc = _lib.load().rtb200_mh_moves_device(
+        _ptr(k, i32), _ptr(voro, f64), _ptr(logL, f64), B, ldk, int(n_moves), _ptr(buf["ivo"], i32),
+        _ptr(buf["iwhich"], i32), _ptr(buf["cauchy"], f64), _ptr(buf["u"][1], f64), _ptr(beta, f64),
+        _ptr(sigma, f64), pr.ctypes.data_as(C.POINTER(C.c_double)), _ptr(src_offset, f64),
+        _ptr(src_depth, f64), _ptr(tobs, f64), src_offset.numel(), _ptr(buf["accept"], i32),
+        st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle())
+    _lib.check(rc)
+    pos.copy_(((pos.to(torch.int64) + n_moves) % period).to(i32))
+    return (buf["accept"] == 1).sum(dim=0)
 
 
 def mcmc_step_device(k, voro, logL, sigma, beta, prior, sd_prior, pk, kmin, kmax, src_offset,

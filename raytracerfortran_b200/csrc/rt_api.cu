@@ -25,6 +25,7 @@ using rtb::TileCfg;
 constexpr double kPi = 3.141592653589793238462643383279502884197;  // data_type.f90:5 (PI2)
 constexpr int    kMaxChunks = 64;
 constexpr int    kSchedSlots = 256;  // tile-scheduler counter pairs, one per launch in flight
+constexpr int    kGraphSlots = 512;  // further pairs owned by the kernel nodes of a captured graph
 constexpr int    kDeepLdv = 40;     // models with this many velocities or more use the deep-model kernel
 
 struct DevBuf {
@@ -58,6 +59,10 @@ struct Ctx {
         idxar, arparb, sched, mh_ll, mh_out, mh_kp, mh_lpr;
     unsigned sched_seq = 0;        // launches take scheduler slots round robin
     bool     sched_dirty = false;  // a CUDA call failed: a kernel may have left counters behind
+    // one cached CUDA graph of a run of MH moves (rtb200_mh_moves_device)
+    cudaGraphExec_t     mv_exec = nullptr;
+    std::vector<size_t> mv_key;
+    cudaStream_t        s_cap = nullptr;
     void  *pin = nullptr;          // pinned staging for small calls
     size_t pin_cap = 0;
     // options (<= 0: automatic)
@@ -133,8 +138,8 @@ int ensure_init(int device = -1) {
     }
     CK(cudaEventCreate(&g.ev_t0));
     CK(cudaEventCreate(&g.ev_t1));
-    CK(g.sched.reserve(kSchedSlots * 2 * sizeof(int)));
-    CK(cudaMemset(g.sched.p, 0, kSchedSlots * 2 * sizeof(int)));
+    CK(g.sched.reserve((kSchedSlots + kGraphSlots) * 2 * sizeof(int)));
+    CK(cudaMemset(g.sched.p, 0, (kSchedSlots + kGraphSlots) * 2 * sizeof(int)));
     g.ok = true;
     g.err.clear();
     return 0;
@@ -147,7 +152,7 @@ int *next_sched() {
     if (g.opt_static_tiles) return nullptr;
     if (g.sched_dirty) {
         cudaDeviceSynchronize();
-        if (cudaMemset(g.sched.p, 0, kSchedSlots * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+        if (cudaMemset(g.sched.p, 0, (kSchedSlots + kGraphSlots) * 2 * sizeof(int)) != cudaSuccess) return nullptr;
         g.sched_dirty = false;
     }
     return g.sched.as<int>() + 2 * (g.sched_seq++ % kSchedSlots);
@@ -724,6 +729,92 @@ int rtb200_mh_step_device(const int *d_k, double *d_voro, double *d_logL, int B,
     return 0;
 }
 
+// n_moves fixed-dimension moves back to back.  A move is three dependent launches (propose,
+// evaluate, accept) of a few hundred microseconds at most, so a run of moves is launch-bound; the
+// run is captured once into a CUDA graph and replayed while the caller keeps passing the same
+// buffers (the key is every pointer and size).  Each kernel node owns its tile-scheduler slot.
+int rtb200_mh_moves_device(const int *d_k, double *d_voro, double *d_logL, int B, int ldk,
+                           int n_moves, const int *d_ivo, const int *d_iwhich,
+                           const double *d_cauchy, const double *d_uacc, const double *d_beta,
+                           const double *d_sigma, const double *prior, const double *d_src_offset,
+                           const double *d_src_depth, const double *d_tobs, int NSrc,
+                           int *d_accept, void *stream) {
+    if (int rc = ensure_init()) return rc;
+    g.err.clear();
+    if (B <= 0 || n_moves <= 0) return 0;
+    if (NSrc <= 0) return fail("rtb200_mh_moves_device needs at least one source");
+    if (ldk < 1 || ldk > 64) return fail("rtb200_mh_moves_device supports 1..64 nodes per state");
+    if (!prior) return fail("rtb200_mh_moves_device needs the prior array");
+    if (n_moves > kGraphSlots) return fail("rtb200_mh_moves_device: at most 512 moves per call");
+    cudaStream_t st = stream ? (cudaStream_t)stream : g.s_comp;
+    TileCfg cfg;
+    if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
+    const size_t Bz = (size_t)B, Bpad = (Bz + cfg.M - 1) / cfg.M * cfg.M + cfg.M;
+    CK(g.vels.reserve(Bpad * ldk * 8));
+    CK(g.depths.reserve(Bpad * ldk * 8));
+    CK(g.nl.reserve(Bpad * 4));
+    CK(g.vsorted.reserve(Bz * 2 * ldk * 8));
+    CK(g.mh_ll.reserve(Bz * 8));
+    CK(g.mh_out.reserve(Bz * 4));
+    std::vector<size_t> key = {(size_t)d_k, (size_t)d_voro, (size_t)d_logL, (size_t)B, (size_t)ldk,
+                               (size_t)n_moves, (size_t)d_ivo, (size_t)d_iwhich, (size_t)d_cauchy,
+                               (size_t)d_uacc, (size_t)d_beta, (size_t)d_sigma, (size_t)d_src_offset,
+                               (size_t)d_src_depth, (size_t)d_tobs, (size_t)NSrc, (size_t)d_accept,
+                               (size_t)g.vels.p, (size_t)g.depths.p, (size_t)g.nl.p,
+                               (size_t)g.vsorted.p, (size_t)g.mh_ll.p, (size_t)g.mh_out.p,
+                               (size_t)cfg.M, (size_t)cfg.grid, (size_t)cfg.variant, (size_t)g.opt_static_tiles};
+    for (int i = 0; i < 7; ++i) {
+        size_t bits;
+        memcpy(&bits, &prior[i], sizeof bits);
+        key.push_back(bits);
+    }
+    if (!g.mv_exec || key != g.mv_key) {
+        if (g.mv_exec) { cudaGraphExecDestroy(g.mv_exec); g.mv_exec = nullptr; }
+        if (!g.s_cap) CK(cudaStreamCreateWithFlags(&g.s_cap, cudaStreamNonBlocking));
+        rtb::MhPrior pr;
+        pr.scale[0] = prior[0]; pr.scale[1] = prior[1];
+        pr.minlim[0] = prior[2]; pr.minlim[1] = prior[3];
+        pr.maxlim[0] = prior[4]; pr.maxlim[1] = prior[5];
+        pr.hmin = prior[6];
+        if (rtb::max_ctas_per_sm(cfg) < 1) return fail("batch kernel cannot be resident");   // sets the smem attribute
+        CK(cudaStreamBeginCapture(g.s_cap, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e = cudaSuccess;
+        for (int m = 0; m < n_moves && e == cudaSuccess; ++m) {
+            const size_t o = (size_t)m * Bz;
+            e = rtb::launch_propose_voro(d_k, d_voro, B, ldk, d_ivo + o, d_iwhich + o, d_cauchy + o, pr,
+                                         g.vels.as<double>(), g.depths.as<double>(), g.nl.as<int>(),
+                                         g.vsorted.as<double>(), g.mh_out.as<int>(), g.s_cap);
+            if (e != cudaSuccess) break;
+            BatchArgs a{};
+            a.vels = g.vels.as<double>(); a.depths = g.depths.as<double>(); a.nlayers = g.nl.as<int>();
+            a.B = B; a.ldv = ldk; a.ldz = ldk; a.kmode = 1;
+            a.src_offset = d_src_offset; a.src_depth = d_src_depth;
+            a.tobs = d_tobs; a.nsrc = NSrc; a.sigma = d_sigma;
+            a.logL = g.mh_ll.as<double>();
+            a.logc = log_norm_const(NSrc);
+            a.padded = 1;
+            a.sched = g.opt_static_tiles ? nullptr : g.sched.as<int>() + 2 * (kSchedSlots + m);
+            e = rtb::launch_batch(a, cfg, g.s_cap);
+            if (e != cudaSuccess) break;
+            e = rtb::launch_mh_accept(d_k, d_voro, g.vsorted.as<double>(), d_logL, g.mh_ll.as<double>(),
+                                      g.mh_out.as<int>(), d_uacc + o, d_beta, B, ldk, d_accept + o, g.s_cap);
+        }
+        cudaGraph_t graph = nullptr;
+        cudaError_t e2 = cudaStreamEndCapture(g.s_cap, &graph);
+        if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail("capturing the MH moves", e); }
+        if (e2 != cudaSuccess) return fail("cudaStreamEndCapture", e2);
+        e = cudaGraphInstantiate(&g.mv_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { g.mv_exec = nullptr; return fail("cudaGraphInstantiate", e); }
+        g.mv_key = key;
+    }
+    CK(cudaGraphLaunch(g.mv_exec, st));
+    g.launches += 3LL * n_moves;
+    g.last = cfg;
+    if (!stream) CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int rtb200_bd_step_device(int *d_k, double *d_voro, double *d_logL, int B, int ldk,
                           const double *d_uk, const int *d_idel, const double *d_uz,
                           const double *d_uv, const double *d_uacc, const double *d_beta,
@@ -858,6 +949,11 @@ void rtb200_shutdown(void) {
     cudaEventDestroy(g.ev_t1);
     cudaStreamDestroy(g.s_comp);
     cudaStreamDestroy(g.s_comp2);
+    if (g.mv_exec) cudaGraphExecDestroy(g.mv_exec);
+    g.mv_exec = nullptr;
+    g.mv_key.clear();
+    if (g.s_cap) cudaStreamDestroy(g.s_cap);
+    g.s_cap = nullptr;
     cudaStreamDestroy(g.s_h2d);
     cudaStreamDestroy(g.s_d2h);
     g.inited = g.ok = false;
