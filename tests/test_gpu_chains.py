@@ -305,3 +305,34 @@ def test_chain_moves_survive_hostile_inputs():
     assert set(np.unique(a2.cpu().numpy())) <= {-1, 0, 1, 2} and set(np.unique(a3.cpu().numpy())) <= {-1, 0, 1, 2}
     kk = tk.cpu().numpy()
     assert np.all((kk[good] >= 1) & (kk[good] <= ldk))
+
+
+def test_mh_moves_graph_replay_and_recapture():
+    """rtb200_mh_moves_device replays its captured graph when called again with the same buffers
+    and captures anew when they change; either way the chains follow the oracle."""
+    import math
+    import torch
+    prior = chains.prior_array()
+    prior[:2] /= 10.0
+    for B, n_moves, calls in ((200, 5, 3), (333, 4, 2), (200, 5, 1)):
+        ldk, nsrc = 6, 12
+        k, voro, so, sd, tobs, sigma, ll = _setup(B, ldk, nsrc, 90 + B)
+        beta = np.ones(B)
+        tk, tv, tl, tb, tg, ts, td, to = _dev(k, voro, ll, beta, sigma, so, sd, tobs)
+        pos = torch.zeros(B, dtype=torch.int32, device="cuda")
+        cur_v, cur_l, p = voro, ll, np.zeros(B, dtype=np.int64)
+        for c in range(calls):
+            gen = torch.Generator(device="cuda").manual_seed(1000 + c)
+            chains.mh_moves_device(tk, tv, tl, pos, n_moves, tb, tg, prior, ts, td, to, generator=gen)
+            gen = torch.Generator(device="cuda").manual_seed(1000 + c)
+            u = torch.empty((2, n_moves, B), dtype=torch.float64, device="cuda").uniform_(generator=gen)
+            cauchy, uacc = torch.tan(math.pi * (u[0] - 0.5)).cpu().numpy(), u[1].cpu().numpy()
+            for m in range(n_moves):
+                j = (p + m) % (2 * k - 1) + 1
+                r = oracle.mh_step_batch(k, cur_v, cur_l, (j // 2 + 1).astype(np.int32),
+                                         (j % 2 + 1).astype(np.int32), cauchy[m], uacc[m], beta, sigma,
+                                         prior, so, sd, tobs)
+                cur_v, cur_l = r["voro"], r["logL"]
+            p = (p + n_moves) % (2 * k - 1)
+            assert np.array_equal(tv.cpu().numpy().view(np.uint64), cur_v.view(np.uint64)), (B, c)
+            assert np.array_equal(pos.cpu().numpy(), p)
