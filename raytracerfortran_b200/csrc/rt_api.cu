@@ -674,6 +674,49 @@ int rtb200_dff_batch_device(const double *d_vels, const double *d_depths, const 
     return 0;
 }
 
+namespace {
+
+rtb::MhPrior make_prior(const double *prior) {
+    rtb::MhPrior pr;
+    pr.scale[0] = prior[0]; pr.scale[1] = prior[1];
+    pr.minlim[0] = prior[2]; pr.minlim[1] = prior[3];
+    pr.maxlim[0] = prior[4]; pr.maxlim[1] = prior[5];
+    pr.hmin = prior[6];
+    return pr;
+}
+
+// Scratch of a chain move: the proposal as (vp, ziface) rows for the batch kernel, its node count,
+// its sorted nodes, its logL and the outside / no-move code.
+int reserve_move_scratch(int B, int ldk, const TileCfg &cfg) {
+    const size_t Bz = (size_t)B, Bpad = (Bz + cfg.M - 1) / cfg.M * cfg.M + cfg.M;
+    CK(g.vels.reserve(Bpad * ldk * 8));
+    CK(g.depths.reserve(Bpad * ldk * 8));
+    CK(g.nl.reserve(Bpad * 4));
+    CK(g.vsorted.reserve(Bz * 2 * ldk * 8));
+    CK(g.mh_ll.reserve(Bz * 8));
+    CK(g.mh_out.reserve(Bz * 4));
+    CK(g.mh_kp.reserve(Bz * 4));
+    CK(g.mh_lpr.reserve(Bz * 8));
+    return 0;
+}
+
+// The batch kernel's arguments for evaluating the scratch rows in k-mode; logL goes to g.mh_ll.
+BatchArgs move_eval_args(int B, int ldk, const double *d_src_offset, const double *d_src_depth,
+                         const double *d_tobs, int NSrc, const double *d_sigma, int *sched) {
+    BatchArgs a{};
+    a.vels = g.vels.as<double>(); a.depths = g.depths.as<double>(); a.nlayers = g.nl.as<int>();
+    a.B = B; a.ldv = ldk; a.ldz = ldk; a.kmode = 1;
+    a.src_offset = d_src_offset; a.src_depth = d_src_depth;
+    a.tobs = d_tobs; a.nsrc = NSrc; a.sigma = d_sigma;
+    a.logL = g.mh_ll.as<double>();
+    a.logc = log_norm_const(NSrc);
+    a.padded = 1;
+    a.sched = sched;
+    return a;
+}
+
+}  // namespace
+
 int rtb200_mh_step_device(const int *d_k, double *d_voro, double *d_logL, int B, int ldk,
                           const int *d_ivo, const int *d_iwhich, const double *d_cauchy,
                           const double *d_uacc, const double *d_beta, const double *d_sigma,
@@ -689,30 +732,13 @@ int rtb200_mh_step_device(const int *d_k, double *d_voro, double *d_logL, int B,
     cudaStream_t st = stream ? (cudaStream_t)stream : g.s_comp;
     TileCfg cfg;
     if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
-    const size_t Bz = (size_t)B, Bpad = (Bz + cfg.M - 1) / cfg.M * cfg.M + cfg.M;
-    CK(g.vels.reserve(Bpad * ldk * 8));
-    CK(g.depths.reserve(Bpad * ldk * 8));
-    CK(g.nl.reserve(Bpad * 4));
-    CK(g.vsorted.reserve(Bz * 2 * ldk * 8));
-    CK(g.mh_ll.reserve(Bz * 8));
-    CK(g.mh_out.reserve(Bz * 4));
-    rtb::MhPrior pr;
-    pr.scale[0] = prior[0]; pr.scale[1] = prior[1];
-    pr.minlim[0] = prior[2]; pr.minlim[1] = prior[3];
-    pr.maxlim[0] = prior[4]; pr.maxlim[1] = prior[5];
-    pr.hmin = prior[6];
+    if (int rc = reserve_move_scratch(B, ldk, cfg)) return rc;
+    const rtb::MhPrior pr = make_prior(prior);
     CK(rtb::launch_propose_voro(d_k, d_voro, B, ldk, d_ivo, d_iwhich, d_cauchy, pr,
                                 g.vels.as<double>(), g.depths.as<double>(), g.nl.as<int>(),
                                 g.vsorted.as<double>(), g.mh_out.as<int>(), st));
-    BatchArgs a{};
-    a.vels = g.vels.as<double>(); a.depths = g.depths.as<double>(); a.nlayers = g.nl.as<int>();
-    a.B = B; a.ldv = ldk; a.ldz = ldk; a.kmode = 1;
-    a.src_offset = d_src_offset; a.src_depth = d_src_depth;
-    a.tobs = d_tobs; a.nsrc = NSrc; a.sigma = d_sigma;
-    a.logL = g.mh_ll.as<double>();
-    a.logc = log_norm_const(NSrc);
-    a.padded = 1;
-    a.sched = next_sched();
+    const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, d_sigma,
+                                       next_sched());
     CK(cudaEventRecord(g.ev_k0[0], st));
     CK(rtb::launch_batch(a, cfg, st));
     CK(cudaEventRecord(g.ev_k1[0], st));
@@ -749,13 +775,7 @@ int rtb200_mh_moves_device(const int *d_k, double *d_voro, double *d_logL, int B
     cudaStream_t st = stream ? (cudaStream_t)stream : g.s_comp;
     TileCfg cfg;
     if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
-    const size_t Bz = (size_t)B, Bpad = (Bz + cfg.M - 1) / cfg.M * cfg.M + cfg.M;
-    CK(g.vels.reserve(Bpad * ldk * 8));
-    CK(g.depths.reserve(Bpad * ldk * 8));
-    CK(g.nl.reserve(Bpad * 4));
-    CK(g.vsorted.reserve(Bz * 2 * ldk * 8));
-    CK(g.mh_ll.reserve(Bz * 8));
-    CK(g.mh_out.reserve(Bz * 4));
+    if (int rc = reserve_move_scratch(B, ldk, cfg)) return rc;
     std::vector<size_t> key = {(size_t)d_k, (size_t)d_voro, (size_t)d_logL, (size_t)B, (size_t)ldk,
                                (size_t)n_moves, (size_t)d_ivo, (size_t)d_iwhich, (size_t)d_cauchy,
                                (size_t)d_uacc, (size_t)d_beta, (size_t)d_sigma, (size_t)d_src_offset,
@@ -771,29 +791,18 @@ int rtb200_mh_moves_device(const int *d_k, double *d_voro, double *d_logL, int B
     if (!g.mv_exec || key != g.mv_key) {
         if (g.mv_exec) { cudaGraphExecDestroy(g.mv_exec); g.mv_exec = nullptr; }
         if (!g.s_cap) CK(cudaStreamCreateWithFlags(&g.s_cap, cudaStreamNonBlocking));
-        rtb::MhPrior pr;
-        pr.scale[0] = prior[0]; pr.scale[1] = prior[1];
-        pr.minlim[0] = prior[2]; pr.minlim[1] = prior[3];
-        pr.maxlim[0] = prior[4]; pr.maxlim[1] = prior[5];
-        pr.hmin = prior[6];
+        const rtb::MhPrior pr = make_prior(prior);
         if (rtb::max_ctas_per_sm(cfg) < 1) return fail("batch kernel cannot be resident");   // sets the smem attribute
         CK(cudaStreamBeginCapture(g.s_cap, cudaStreamCaptureModeThreadLocal));
         cudaError_t e = cudaSuccess;
         for (int m = 0; m < n_moves && e == cudaSuccess; ++m) {
-            const size_t o = (size_t)m * Bz;
+            const size_t o = (size_t)m * (size_t)B;
             e = rtb::launch_propose_voro(d_k, d_voro, B, ldk, d_ivo + o, d_iwhich + o, d_cauchy + o, pr,
                                          g.vels.as<double>(), g.depths.as<double>(), g.nl.as<int>(),
                                          g.vsorted.as<double>(), g.mh_out.as<int>(), g.s_cap);
             if (e != cudaSuccess) break;
-            BatchArgs a{};
-            a.vels = g.vels.as<double>(); a.depths = g.depths.as<double>(); a.nlayers = g.nl.as<int>();
-            a.B = B; a.ldv = ldk; a.ldz = ldk; a.kmode = 1;
-            a.src_offset = d_src_offset; a.src_depth = d_src_depth;
-            a.tobs = d_tobs; a.nsrc = NSrc; a.sigma = d_sigma;
-            a.logL = g.mh_ll.as<double>();
-            a.logc = log_norm_const(NSrc);
-            a.padded = 1;
-            a.sched = g.opt_static_tiles ? nullptr : g.sched.as<int>() + 2 * (kSchedSlots + m);
+            const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, d_sigma,
+                                               g.opt_static_tiles ? nullptr : g.sched.as<int>() + 2 * (kSchedSlots + m));
             e = rtb::launch_batch(a, cfg, g.s_cap);
             if (e != cudaSuccess) break;
             e = rtb::launch_mh_accept(d_k, d_voro, g.vsorted.as<double>(), d_logL, g.mh_ll.as<double>(),
@@ -831,20 +840,8 @@ int rtb200_bd_step_device(int *d_k, double *d_voro, double *d_logL, int B, int l
     cudaStream_t st = stream ? (cudaStream_t)stream : g.s_comp;
     TileCfg cfg;
     if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
-    const size_t Bz = (size_t)B, Bpad = (Bz + cfg.M - 1) / cfg.M * cfg.M + cfg.M;
-    CK(g.vels.reserve(Bpad * ldk * 8));
-    CK(g.depths.reserve(Bpad * ldk * 8));
-    CK(g.nl.reserve(Bpad * 4));
-    CK(g.vsorted.reserve(Bz * 2 * ldk * 8));
-    CK(g.mh_ll.reserve(Bz * 8));
-    CK(g.mh_out.reserve(Bz * 4));
-    CK(g.mh_kp.reserve(Bz * 4));
-    CK(g.mh_lpr.reserve(Bz * 8));
-    rtb::MhPrior pr;
-    pr.scale[0] = prior[0]; pr.scale[1] = prior[1];
-    pr.minlim[0] = prior[2]; pr.minlim[1] = prior[3];
-    pr.maxlim[0] = prior[4]; pr.maxlim[1] = prior[5];
-    pr.hmin = prior[6];
+    if (int rc = reserve_move_scratch(B, ldk, cfg)) return rc;
+    const rtb::MhPrior pr = make_prior(prior);
     rtb::BdPrior bd{};
     bd.kmin = kmin; bd.kmax = kmax; bd.use_pk = pk ? 1 : 0;
     for (int i = kmin; pk && i <= kmax; ++i) bd.logpk[i - 1] = std::log(pk[i - 1]);   // LOG(pk(i)), libm
@@ -852,15 +849,8 @@ int rtb200_bd_step_device(int *d_k, double *d_voro, double *d_logL, int B, int l
                               g.vels.as<double>(), g.depths.as<double>(), g.nl.as<int>(),
                               g.mh_kp.as<int>(), g.vsorted.as<double>(), g.mh_lpr.as<double>(),
                               g.mh_out.as<int>(), st));
-    BatchArgs a{};
-    a.vels = g.vels.as<double>(); a.depths = g.depths.as<double>(); a.nlayers = g.nl.as<int>();
-    a.B = B; a.ldv = ldk; a.ldz = ldk; a.kmode = 1;
-    a.src_offset = d_src_offset; a.src_depth = d_src_depth;
-    a.tobs = d_tobs; a.nsrc = NSrc; a.sigma = d_sigma;
-    a.logL = g.mh_ll.as<double>();
-    a.logc = log_norm_const(NSrc);
-    a.padded = 1;
-    a.sched = next_sched();
+    const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, d_sigma,
+                                       next_sched());
     CK(cudaEventRecord(g.ev_k0[0], st));
     CK(rtb::launch_batch(a, cfg, st));
     CK(cudaEventRecord(g.ev_k1[0], st));
@@ -892,25 +882,12 @@ int rtb200_sd_step_device(const int *d_k, const double *d_voro, double *d_logL, 
     cudaStream_t st = stream ? (cudaStream_t)stream : g.s_comp;
     TileCfg cfg;
     if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
-    const size_t Bz = (size_t)B, Bpad = (Bz + cfg.M - 1) / cfg.M * cfg.M + cfg.M;
-    CK(g.vels.reserve(Bpad * ldk * 8));
-    CK(g.depths.reserve(Bpad * ldk * 8));
-    CK(g.nl.reserve(Bpad * 4));
-    CK(g.mh_ll.reserve(Bz * 8));
-    CK(g.mh_out.reserve(Bz * 4));
-    CK(g.mh_lpr.reserve(Bz * 8));
+    if (int rc = reserve_move_scratch(B, ldk, cfg)) return rc;
     CK(rtb::launch_propose_sd(d_k, d_voro, B, ldk, d_sigma, d_ugate, d_gauss, sd_prior[0],
                               sd_prior[1], sd_prior[2], g.vels.as<double>(), g.depths.as<double>(),
                               g.nl.as<int>(), g.mh_lpr.as<double>(), g.mh_out.as<int>(), st));
-    BatchArgs a{};
-    a.vels = g.vels.as<double>(); a.depths = g.depths.as<double>(); a.nlayers = g.nl.as<int>();
-    a.B = B; a.ldv = ldk; a.ldz = ldk; a.kmode = 1;
-    a.src_offset = d_src_offset; a.src_depth = d_src_depth;
-    a.tobs = d_tobs; a.nsrc = NSrc; a.sigma = g.mh_lpr.as<double>();
-    a.logL = g.mh_ll.as<double>();
-    a.logc = log_norm_const(NSrc);
-    a.padded = 1;
-    a.sched = next_sched();
+    const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, g.mh_lpr.as<double>(),
+                                       next_sched());
     CK(cudaEventRecord(g.ev_k0[0], st));
     CK(rtb::launch_batch(a, cfg, st));
     CK(cudaEventRecord(g.ev_k1[0], st));
