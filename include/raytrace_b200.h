@@ -194,6 +194,23 @@ int rtb200_sd_step_device(const int *d_k, const double *d_voro, double *d_logL, 
                           const double *d_src_offset, const double *d_src_depth,
                           const double *d_tobs, int NSrc, int *d_accept, void *stream);
 
+/* The AR(1) move of EXPLORE_MH (prjmh_temper_rf.f90:583-631, IAR = 1) for B independent chains on
+ * the device, with PROPOSAL_ARRT (:1521-1552): a chain without an AR parameter proposes its birth
+ * (uniform over [minlimarRT, maxlimarRT], logarp = LOG(0.5)); otherwise death when the choice
+ * uniform is >= 0.5 (logarp = LOG(2)) or a perturbation arparRT + pertarsdRT*gauss (logarp = 0).
+ * The model is re-evaluated with the proposal (loglhood.f90:171-182) and the move is rejected iff
+ * ran_uni >= EXP(logarp + (logL_new - logL)*beta_mh).  d_logL must be the likelihood under the
+ * chain's current (idxar, arpar).
+ *   d_idxar [B], d_arpar [B] in/out;  d_uchoice, d_uprop, d_uacc [B] uniforms;  d_gauss [B] normal
+ *   ar_prior HOST [4] = pertarsdRT, minlimarRT, maxlimarRT, armxRT      (read_input.f90:223-227)
+ *   d_accept [B] out: 1 accepted, 0 rejected, -1 outside the bounds */
+int rtb200_ar_step_device(const int *d_k, const double *d_voro, double *d_logL,
+                          const double *d_sigma, int *d_idxar, double *d_arpar, int B, int ldk,
+                          const double *d_uchoice, const double *d_uprop, const double *d_gauss,
+                          const double *d_uacc, const double *d_beta, const double *ar_prior,
+                          const double *d_src_offset, const double *d_src_depth,
+                          const double *d_tobs, int NSrc, int *d_accept, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Runtime control and introspection
  * ---------------------------------------------------------------------------------------- */

@@ -79,6 +79,9 @@ def lib():
         _lib.orc_sd_step_batch.restype = None
         _lib.orc_sd_step_batch.argtypes = [ip, dp, dp, dp, C.c_int, C.c_int, dp, dp, dp, dp, dp,
                                            dp, dp, C.c_int, dp, ip, dp]
+        _lib.orc_ar_step_batch.restype = None
+        _lib.orc_ar_step_batch.argtypes = [ip, dp, dp, dp, ip, dp, C.c_int, C.c_int, dp, dp, dp, dp, dp,
+                                           dp, dp, dp, C.c_int, dp, ip, dp]
         _lib.orc_batch_stats.restype = None
         _lib.orc_batch_stats.argtypes = [dp, dp, ip, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int,
                                          C.POINTER(Stats)]
@@ -197,6 +200,27 @@ def sd_step_batch(k, voro, logL, sigma, u_gate, gauss, u_acc, beta, sd_prior, sr
                             _p(_d(gauss)), _p(_d(u_acc)), _p(_d(beta)), _p(_d(sd_prior)), _p(so), _p(sd),
                             so.size, _p(ob), acc.ctypes.data_as(I), _p(llp))
     return {"logL": ll, "sigma": sg, "accept": acc, "logL_prop": llp}
+
+
+def ar_step_batch(k, voro, logL, sigma, idxar, arpar, u_choice, u_prop, gauss, u_acc, beta, ar_prior,
+                  src_offset, src_depth, tobs):
+    """The AR(1) move of B independent chains (orc_ar_step_batch).  Returns a dict with the updated
+    copies of logL, idxar, arpar, `accept` [B] (1 / 0 / -1 outside) and `logL_prop`."""
+    kk = np.ascontiguousarray(k, dtype=np.int32)
+    vo = _d(voro)
+    ll = np.array(logL, dtype=np.float64, copy=True)
+    ia = np.array(idxar, dtype=np.int32, copy=True)
+    ap = np.array(arpar, dtype=np.float64, copy=True)
+    B, two, ldk = vo.shape
+    so, sd, ob = _d(src_offset), _d(src_depth), _d(tobs)
+    acc = np.zeros(B, dtype=np.int32)
+    llp = np.full(B, np.nan)
+    I = C.POINTER(C.c_int)
+    lib().orc_ar_step_batch(kk.ctypes.data_as(I), _p(vo), _p(ll), _p(_d(sigma)), ia.ctypes.data_as(I), _p(ap),
+                            B, ldk, _p(_d(u_choice)), _p(_d(u_prop)), _p(_d(gauss)), _p(_d(u_acc)),
+                            _p(_d(beta)), _p(_d(ar_prior)), _p(so), _p(sd), so.size, _p(ob),
+                            acc.ctypes.data_as(I), _p(llp))
+    return {"logL": ll, "idxar": ia, "arpar": ap, "accept": acc, "logL_prop": llp}
 
 
 def loglhood_voro(node_depth, node_vp, src_offset, src_depth, tobs, sigma):

@@ -709,6 +709,66 @@ void orc_sd_step_batch(const int *k, const double *voro, double *logL, double *s
     }
 }
 
+/* ---- the AR(1) move of EXPLORE_MH (:583-631, IAR = 1) with PROPOSAL_ARRT (:1521-1552) --------- *
+ * idxarRT == 0: birth (arparRT uniform over [minlimarRT, maxlimarRT], logarp = LOG(0.5));
+ * else ran_uni_ar >= 0.5: death (idxarRT = 0, arparRT = minlimarRT - 1, logarp = LOG(2)),
+ * otherwise perturb (arparRT + pertarsdRT*gauss, logarp = 0).  LOGLHOOD with the AR model of
+ * loglhood.f90:171-182; reject iff ran_uni >= EXP(logarp + (logL_new - logL)*beta_mh).
+ * ar_prior = { pertarsdRT, minlimarRT, maxlimarRT, armxRT }.  Returns 1 / 0 / -1 outside.     */
+int orc_ar_step(int k, const double *node_depth, const double *node_vp, double *logL, double sigma,
+                int *idxar, double *arpar, double u_choice, double u_prop, double gauss,
+                double u_acc, double beta, const double *ar_prior,
+                const double *src_offset, const double *src_depth, int nsrc, const double *tobs,
+                double *logL_prop)
+{
+    const double pert = ar_prior[0], amin = ar_prior[1], amax = ar_prior[2], armx = ar_prior[3];
+    int idx_new, outside = 0;
+    double ar_new, logarp;
+    if (*idxar == 0) {                                           /* :588-591, :1531-1537 */
+        logarp = log(0.5);
+        ar_new = u_prop * (amax - amin) + amin;
+        idx_new = 1;
+        if ((ar_new - amin) < 0.0 || (amax - ar_new) < 0.0) outside = 1;
+    } else if (u_choice >= 0.5) {                                /* :594-597, :1539-1542 */
+        logarp = log(2.0);
+        ar_new = amin - 1.0;
+        idx_new = 0;
+    } else {                                                     /* :598-601, :1544-1549 */
+        logarp = 0.0;
+        ar_new = *arpar + pert * gauss;
+        idx_new = *idxar;
+        if ((ar_new - amin) < 0.0 || (amax - ar_new) < 0.0) outside = 1;
+    }
+    if (outside) return -1;                                      /* :621-625 */
+    double *pred = (double *)malloc(sizeof(double) * (size_t)(nsrc > 0 ? nsrc : 1));
+    orc_loglhood_rt(k, node_vp, node_depth + 1, src_offset, src_depth, nsrc, tobs, sigma, pred);
+    const double ll = orc_loglhood_from_times_ar(pred, tobs, nsrc, sigma, idx_new, ar_new, armx);
+    free(pred);
+    if (logL_prop) *logL_prop = ll;
+    const double logPLratio = logarp + (ll - *logL) * beta;      /* :611 */
+    if (u_acc >= exp(logPLratio)) return 0;                      /* :613-615 */
+    *idxar = idx_new;                                            /* :617 */
+    *arpar = ar_new;
+    *logL = ll;
+    return 1;
+}
+
+void orc_ar_step_batch(const int *k, const double *voro, double *logL, const double *sigma,
+                       int *idxar, double *arpar, int B, int ldk, const double *u_choice,
+                       const double *u_prop, const double *gauss, const double *u_acc,
+                       const double *beta, const double *ar_prior,
+                       const double *src_offset, const double *src_depth, int nsrc,
+                       const double *tobs, int *accept, double *logL_prop)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int b = 0; b < B; ++b) {
+        const double *row = voro + (size_t)b * 2 * ldk;
+        accept[b] = orc_ar_step(k[b], row, row + ldk, &logL[b], sigma[b], &idxar[b], &arpar[b],
+                                u_choice[b], u_prop[b], gauss[b], u_acc[b], beta[b], ar_prior,
+                                src_offset, src_depth, nsrc, tobs, logL_prop ? &logL_prop[b] : NULL);
+    }
+}
+
 /* B independent chains, one move each; voro [B][2][ldk] (depth row, vp row), OpenMP over chains. */
 void orc_mh_step_batch(const int *k, double *voro, double *logL, int B, int ldk,
                        const int *ivo, const int *iwhich, const double *cauchy, const double *u_acc,

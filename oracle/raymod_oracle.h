@@ -144,6 +144,19 @@ void orc_sd_step_batch(const int *k, const double *voro, double *logL, double *s
                        const double *src_offset, const double *src_depth, int nsrc,
                        const double *tobs, int *accept, double *logL_prop);
 
+/* N2 + N4: the AR(1) move of EXPLORE_MH (:583-631) with PROPOSAL_ARRT (:1521-1552). */
+int orc_ar_step(int k, const double *node_depth, const double *node_vp, double *logL, double sigma,
+                int *idxar, double *arpar, double u_choice, double u_prop, double gauss,
+                double u_acc, double beta, const double *ar_prior,
+                const double *src_offset, const double *src_depth, int nsrc, const double *tobs,
+                double *logL_prop);
+void orc_ar_step_batch(const int *k, const double *voro, double *logL, const double *sigma,
+                       int *idxar, double *arpar, int B, int ldk, const double *u_choice,
+                       const double *u_prop, const double *gauss, const double *u_acc,
+                       const double *beta, const double *ar_prior,
+                       const double *src_offset, const double *src_depth, int nsrc,
+                       const double *tobs, int *accept, double *logL_prop);
+
 /* "Next" row N4: LOGLHOOD_RT's likelihood with the AR(1) residual model of IAR = 1
  * (loglhood.f90:171-182, ARPRED_RT :616-653, CHECKBOUNDS_ARMXRT :678-699). */
 double orc_loglhood_from_times_ar(const double *tpred, const double *tobs, int ndat, double sigma,

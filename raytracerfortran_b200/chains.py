@@ -8,7 +8,7 @@ every chain's Markov kernel unchanged.  Chain states live in HBM between moves: 
 voro [B, 2, ldk] float64 (row 0 node depths, row 1 vp, sorted by depth), logL [B], beta [B],
 sigma [B].  torch supplies the tensors, the stream and the random numbers; the move itself is the
 library's kernels.  The birth/death move (BIRTH_FULL /
-DEATH_FULL, :658-710) is `bd_step_device`, the data-error move of EXPLORE_MH (:545-575) `sd_step_device`.
+DEATH_FULL, :658-710) is `bd_step_device`, the data-error move of EXPLORE_MH (:545-575) `sd_step_device`, its AR(1) move (:583-631) `ar_step_device`.
 """
 import math
 
@@ -144,6 +144,40 @@ def sd_step_device(k, voro, logL, sigma, u_gate, gauss, u_acc, beta, sd_prior, s
     rc = _lib.load().rtb200_sd_step_device(
         _ptr(k, i32), _ptr(voro, f64), _ptr(logL, f64), _ptr(sigma, f64), B, ldk, _ptr(u_gate, f64),
         _ptr(gauss, f64), _ptr(u_acc, f64), _ptr(beta, f64), sp.ctypes.data_as(C.POINTER(C.c_double)),
+        _ptr(src_offset, f64), _ptr(src_depth, f64), _ptr(tobs, f64), src_offset.numel(),
+        _ptr(accept, i32), st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle())
+    _lib.check(rc)
+    return accept
+
+
+def ar_prior_array(minlimar=-0.5, maxlimar=0.9, pertarsdsc=10.0, armx=0.5):
+    """pertarsdRT, minlimarRT, maxlimarRT, armxRT: read_input.f90:223-227 (pertarsdRT =
+    (maxlimarRT - minlimarRT)/10) and rjmcmc_com.f90:93 (armxRT = 0.5)."""
+    lo, hi = np.float64(minlimar), np.float64(maxlimar)
+    return np.array([(hi - lo) / np.float64(pertarsdsc), lo, hi, armx], dtype=np.float64)
+
+
+def ar_step_device(k, voro, logL, sigma, idxar, arpar, u_choice, u_prop, gauss, u_acc, beta, ar_prior,
+                   src_offset, src_depth, tobs, accept=None, stream=None):
+    """The AR(1) move of every chain (rtb200_ar_step_device, IAR = 1), in place on idxar [B] i32,
+    arpar [B] f64 and logL.  Returns accept [B] i32: 1 / 0 / -1 outside."""
+    if not voro.is_cuda:
+        raise ValueError("ar_step_device needs CUDA tensors (there is no CPU path)")
+    dev = voro.device
+    _ensure_device(dev.index if dev.index is not None else torch.cuda.current_device())
+    B, two, ldk = voro.shape
+    f64, i32 = torch.float64, torch.int32
+    if accept is None:
+        accept = torch.empty((B,), dtype=i32, device=dev)
+    ap = np.ascontiguousarray(ar_prior, dtype=np.float64)
+    if ap.size != 4:
+        raise ValueError("ar_prior must hold 4 doubles (see ar_prior_array)")
+    import ctypes as C
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    rc = _lib.load().rtb200_ar_step_device(
+        _ptr(k, i32), _ptr(voro, f64), _ptr(logL, f64), _ptr(sigma, f64), _ptr(idxar, i32),
+        _ptr(arpar, f64), B, ldk, _ptr(u_choice, f64), _ptr(u_prop, f64), _ptr(gauss, f64),
+        _ptr(u_acc, f64), _ptr(beta, f64), ap.ctypes.data_as(C.POINTER(C.c_double)),
         _ptr(src_offset, f64), _ptr(src_depth, f64), _ptr(tobs, f64), src_offset.numel(),
         _ptr(accept, i32), st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle())
     _lib.check(rc)

@@ -904,6 +904,50 @@ int rtb200_sd_step_device(const int *d_k, const double *d_voro, double *d_logL, 
     return 0;
 }
 
+int rtb200_ar_step_device(const int *d_k, const double *d_voro, double *d_logL,
+                          const double *d_sigma, int *d_idxar, double *d_arpar, int B, int ldk,
+                          const double *d_uchoice, const double *d_uprop, const double *d_gauss,
+                          const double *d_uacc, const double *d_beta, const double *ar_prior,
+                          const double *d_src_offset, const double *d_src_depth,
+                          const double *d_tobs, int NSrc, int *d_accept, void *stream) {
+    if (int rc = ensure_init()) return rc;
+    g.err.clear();
+    if (B <= 0) return 0;
+    if (NSrc <= 0) return fail("rtb200_ar_step_device needs at least one source");
+    if (ldk < 1 || ldk > 64) return fail("rtb200_ar_step_device supports 1..64 nodes per state");
+    if (!ar_prior) return fail("rtb200_ar_step_device needs the ar_prior array");
+    cudaStream_t st = stream ? (cudaStream_t)stream : g.s_comp;
+    TileCfg cfg;
+    if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
+    if (int rc = reserve_move_scratch(B, ldk, cfg)) return rc;
+    CK(g.idxar.reserve((size_t)B * 4));
+    CK(g.arparb.reserve((size_t)B * 8));
+    CK(rtb::launch_propose_ar(d_k, d_voro, B, ldk, d_idxar, d_arpar, d_uchoice, d_uprop, d_gauss,
+                              ar_prior[0], ar_prior[1], ar_prior[2], std::log(0.5), std::log(2.0),
+                              g.vels.as<double>(), g.depths.as<double>(), g.nl.as<int>(),
+                              g.idxar.as<int>(), g.arparb.as<double>(), g.mh_lpr.as<double>(),
+                              g.mh_out.as<int>(), st));
+    BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, d_sigma, next_sched());
+    a.idxar = g.idxar.as<int>();
+    a.arpar = g.arparb.as<double>();
+    a.armx  = ar_prior[3];
+    CK(cudaEventRecord(g.ev_k0[0], st));
+    CK(rtb::launch_batch(a, cfg, st));
+    CK(cudaEventRecord(g.ev_k1[0], st));
+    CK(rtb::launch_ar_accept(d_idxar, d_arpar, g.idxar.as<int>(), g.arparb.as<double>(),
+                             g.mh_lpr.as<double>(), d_logL, g.mh_ll.as<double>(), g.mh_out.as<int>(),
+                             d_uacc, d_beta, B, d_accept, st));
+    g.launches += 3;
+    g.last = cfg;
+    if (!stream) {
+        CK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, g.ev_k0[0], g.ev_k1[0]));
+        g.kernel_ms = g.total_ms = ms;
+    }
+    return 0;
+}
+
 int rtb200_init(int device) { return ensure_init(device); }
 
 void rtb200_shutdown(void) {

@@ -97,6 +97,16 @@ cudaError_t launch_propose_sd(const int *k, const double *voro, int B, int ldk, 
 cudaError_t launch_sd_accept(double *sigma, const double *sigma_prop, double *logL,
                              const double *logL_prop, const int *outside, const double *u_acc,
                              const double *beta, int B, int *accept, cudaStream_t st);
+cudaError_t launch_propose_ar(const int *k, const double *voro, int B, int ldk, const int *idxar,
+                              const double *arpar, const double *u_choice, const double *u_prop,
+                              const double *gauss, double pert, double amin, double amax,
+                              double log_half, double log_two, double *vels, double *depths,
+                              int *keval, int *idx_prop, double *ar_prop, double *logarp,
+                              int *outside, cudaStream_t st);
+cudaError_t launch_ar_accept(int *idxar, double *arpar, const int *idx_prop, const double *ar_prop,
+                             const double *logarp, double *logL, const double *logL_prop,
+                             const int *outside, const double *u_acc, const double *beta, int B,
+                             int *accept, cudaStream_t st);
 int         max_ctas_per_sm(const TileCfg &c);   // occupancy of the batch kernel for this geometry
 cudaError_t fp64_peak(double *tflops, int repeats, cudaStream_t st);
 cudaError_t fastpath_selftest(double samples, unsigned long long seed, double *mismatches,

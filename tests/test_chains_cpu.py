@@ -194,3 +194,34 @@ def test_sigma_move_rules(cfg1):
     thr = math.exp(r["logL_prop"][0] - ll0[0])
     assert 0 < thr < 1
     assert step(0.5, 2.0, thr * 1.001)["accept"][0] == 0 and step(0.5, 2.0, thr * 0.999)["accept"][0] == 1
+
+
+def test_ar_move_rules(cfg1):
+    """EXPLORE_MH :583-631 with PROPOSAL_ARRT :1521-1552 (IAR = 1)."""
+    voro, k = cfg1["voro"], cfg1["k"]
+    so, sd = cfg1["so"], cfg1["sd"]
+    tobs = cfg1["tobs"] + np.random.default_rng(4).normal(0, 0.016, len(so))
+    ap = chains.ar_prior_array()
+    assert ap.tolist() == [(0.9 - -0.5) / 10.0, -0.5, 0.9, 0.5]
+    pred = oracle.loglhood_rt(voro[0, 1, :k], voro[0, 0, 1:k], so, sd, tobs, 0.02)[1]
+    ll_of = lambda idx, a: oracle.loglhood_from_times_ar(pred, tobs, 0.02, idx, a, 0.5)
+    one = lambda x, dt=np.float64: np.array([x], dtype=dt)
+
+    def step(idx, a, uc, up, g, ua):
+        return oracle.ar_step_batch([k], voro, one(ll_of(idx, a)), one(0.02), one(idx, np.int32), one(a), one(uc),
+                                    one(up), one(g), one(ua), one(1.0), ap, so, sd, tobs)
+    # no AR parameter yet: birth, uniform over the prior, threshold carries LOG(0.5)
+    r = step(0, -1.5, 0.9, 0.25, 0.0, 0.0)
+    a_new = 0.25 * (0.9 - -0.5) + -0.5
+    assert r["accept"][0] == 1 and r["idxar"][0] == 1 and r["arpar"][0] == a_new
+    assert r["logL"][0] == ll_of(1, a_new)
+    thr = math.exp(math.log(0.5) + ll_of(1, a_new) - ll_of(0, -1.5))
+    if 0 < thr < 1:
+        assert step(0, -1.5, 0.9, 0.25, 0.0, thr * 1.001)["accept"][0] == 0
+    # AR on: choice uniform >= 0.5 proposes death (arpar = minlim - 1, LOG(2)), below 0.5 a perturbation
+    r = step(1, 0.3, 0.7, 0.0, 0.0, 0.0)
+    assert r["accept"][0] == 1 and r["idxar"][0] == 0 and r["arpar"][0] == -1.5 and r["logL"][0] == ll_of(0, -1.5)
+    r = step(1, 0.3, 0.2, 0.0, 1.0, 0.0)
+    assert r["accept"][0] == 1 and r["idxar"][0] == 1 and r["arpar"][0] == 0.3 + ap[0] * 1.0
+    assert step(1, 0.3, 0.2, 0.0, 5.0, 0.0)["accept"][0] == -1       # 1.0 > maxlimarRT
+    assert step(1, 0.3, 0.2, 0.0, -6.0, 0.0)["accept"][0] == -1      # -0.54 < minlimarRT

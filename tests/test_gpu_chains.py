@@ -336,3 +336,40 @@ def test_mh_moves_graph_replay_and_recapture():
             p = (p + n_moves) % (2 * k - 1)
             assert np.array_equal(tv.cpu().numpy().view(np.uint64), cur_v.view(np.uint64)), (B, c)
             assert np.array_equal(pos.cpu().numpy(), p)
+
+
+def test_ar_step_matches_oracle():
+    """rtb200_ar_step_device (the AR(1) move, :583-631, IAR = 1) against the oracle, ten moves in a row."""
+    import torch
+    B, ldk, nsrc = 2000, 10, 24
+    k, voro, so, sd, tobs, sigma, _ = _setup(B, ldk, nsrc, 71)
+    rng = np.random.default_rng(72)
+    ap = chains.ar_prior_array()
+    ap[3] = 5.0                                               # a roomy armxRT: most proposals are evaluated
+    beta = 1.0 / 1.4 ** rng.integers(0, 6, B)
+    idxar = rng.integers(0, 2, B).astype(np.int32)
+    arpar = np.where(idxar == 1, rng.uniform(-0.5, 0.9, B), -1.5)
+    ll = np.empty(B)
+    for b in range(B):
+        pred = oracle.loglhood_rt(voro[b, 1, :k[b]], voro[b, 0, 1:k[b]], so, sd, tobs, sigma[b])[1]
+        ll[b] = oracle.loglhood_from_times_ar(pred, tobs, sigma[b], int(idxar[b]), float(arpar[b]), 5.0)
+    tk, tv, tl, tg, ti, ta, tb, ts, td, to = _dev(k, voro, ll, sigma, idxar, arpar, beta, so, sd, tobs)
+    cur_l, cur_i, cur_a = ll, idxar, arpar
+    seen = {1: 0, 0: 0, -1: 0}
+    for step in range(10):
+        u = rng.random((3, B))
+        gauss = rng.standard_normal(B)
+        r = oracle.ar_step_batch(k, voro, cur_l, sigma, cur_i, cur_a, u[0], u[1], gauss, u[2], beta, ap, so, sd, tobs)
+        tu0, tu1, tga, tu2 = _dev(u[0], u[1], gauss, u[2])
+        acc = chains.ar_step_device(tk, tv, tl, tg, ti, ta, tu0, tu1, tga, tu2, tb, ap, ts, td, to).cpu().numpy()
+        assert np.array_equal(acc, r["accept"]), f"step {step}"
+        assert np.array_equal(ti.cpu().numpy(), r["idxar"])
+        assert np.array_equal(ta.cpu().numpy().view(np.uint64), r["arpar"].view(np.uint64))
+        cur_l, cur_i, cur_a = r["logL"], r["idxar"], r["arpar"]
+        for c in seen:
+            seen[c] += int((acc == c).sum())
+    assert all(n > 50 for n in seen.values()), seen
+    got = tl.cpu().numpy()
+    fin = np.isfinite(cur_l) & (np.abs(cur_l) < 1e300)
+    assert np.all(np.abs(got[fin] - cur_l[fin]) <= 1e-11 * np.maximum(np.abs(cur_l[fin]), nsrc * np.abs(np.log(sigma[fin]))))
+    assert np.array_equal(got[~fin], cur_l[~fin])
