@@ -194,6 +194,13 @@ int rtb200_sd_step_device(const int *d_k, const double *d_voro, double *d_logL, 
                           const double *d_src_offset, const double *d_src_depth,
                           const double *d_tobs, int NSrc, int *d_accept, void *stream);
 
+/* IAR = 1 for the chain move entries: register the chains' AR(1) state (device arrays idxarRT [B],
+ * arparRT [B], and armxRT); from then on rtb200_mh_step_device, rtb200_mh_moves_device,
+ * rtb200_bd_step_device and rtb200_sd_step_device evaluate LOGLHOOD with the AR residual model
+ * (loglhood.f90:171-182) of each chain, as the sampler does when IAR = 1.  NULL, NULL returns to
+ * IAR = 0.  rtb200_ar_step_device updates the same arrays when they are the ones passed to it. */
+int rtb200_set_chain_ar(const int *d_idxar, const double *d_arpar, double armx);
+
 /* The AR(1) move of EXPLORE_MH (prjmh_temper_rf.f90:583-631, IAR = 1) for B independent chains on
  * the device, with PROPOSAL_ARRT (:1521-1552): a chain without an AR parameter proposes its birth
  * (uniform over [minlimarRT, maxlimarRT], logarp = LOG(0.5)); otherwise death when the choice

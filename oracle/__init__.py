@@ -82,6 +82,8 @@ def lib():
         _lib.orc_ar_step_batch.restype = None
         _lib.orc_ar_step_batch.argtypes = [ip, dp, dp, dp, ip, dp, C.c_int, C.c_int, dp, dp, dp, dp, dp,
                                            dp, dp, dp, C.c_int, dp, ip, dp]
+        _lib.orc_set_chain_ar.restype = None
+        _lib.orc_set_chain_ar.argtypes = [ip, dp, C.c_double]
         _lib.orc_batch_stats.restype = None
         _lib.orc_batch_stats.argtypes = [dp, dp, ip, C.c_int, C.c_int, C.c_int, dp, dp, C.c_int,
                                          C.POINTER(Stats)]
@@ -221,6 +223,23 @@ def ar_step_batch(k, voro, logL, sigma, idxar, arpar, u_choice, u_prop, gauss, u
                             _p(_d(beta)), _p(_d(ar_prior)), _p(so), _p(sd), so.size, _p(ob),
                             acc.ctypes.data_as(I), _p(llp))
     return {"logL": ll, "idxar": ia, "arpar": ap, "accept": acc, "logL_prop": llp}
+
+
+_chain_ar_keep = None
+
+
+def set_chain_ar(idxar=None, arpar=None, armx=0.5):
+    """IAR = 1 for the *_step_batch functions: the chains' idxarRT / arparRT (copied and kept alive
+    here) enter every likelihood evaluation; call without arguments to return to IAR = 0."""
+    global _chain_ar_keep
+    if idxar is None:
+        _chain_ar_keep = None
+        lib().orc_set_chain_ar(None, None, float(armx))
+        return
+    ia = np.ascontiguousarray(idxar, dtype=np.int32).copy()
+    ap = _d(arpar).copy()
+    _chain_ar_keep = (ia, ap)
+    lib().orc_set_chain_ar(ia.ctypes.data_as(C.POINTER(C.c_int)), _p(ap), float(armx))
 
 
 def loglhood_voro(node_depth, node_vp, src_offset, src_depth, tobs, sigma):

@@ -501,6 +501,34 @@ double orc_loglhood_voro(int k, const double *node_depth, const double *node_vp,
     return ll;
 }
 
+/* Chain likelihood used by the MCMC moves below: LOGLHOOD_RT, with the AR(1) residual model when
+ * the sampler runs with IAR = 1 (the chain's idxarRT / arparRT, loglhood.f90:171-182).  The chains'
+ * AR state is registered with orc_set_chain_ar (NULL: IAR = 0) and indexed by chain.          */
+static const int    *g_ar_idx = NULL;
+static const double *g_ar_par = NULL;
+static double        g_ar_mx  = 0.5;
+
+void orc_set_chain_ar(const int *idxar, const double *arpar, double armx)
+{
+    g_ar_idx = idxar;
+    g_ar_par = arpar;
+    g_ar_mx  = armx;
+}
+
+static double chain_loglhood(int chain, int k, const double *vp, const double *ziface,
+                             const double *src_offset, const double *src_depth, int nsrc,
+                             const double *tobs, double sigma)
+{
+    if (!g_ar_idx || chain < 0)
+        return orc_loglhood_rt(k, vp, ziface, src_offset, src_depth, nsrc, tobs, sigma, NULL);
+    double *pred = (double *)malloc(sizeof(double) * (size_t)(nsrc > 0 ? nsrc : 1));
+    orc_loglhood_rt(k, vp, ziface, src_offset, src_depth, nsrc, tobs, sigma, pred);
+    const double ll = orc_loglhood_from_times_ar(pred, tobs, nsrc, sigma, g_ar_idx[chain],
+                                                 g_ar_par[chain], g_ar_mx);
+    free(pred);
+    return ll;
+}
+
 /* ---- "next" rows N1 + N2: one fixed-dimension Metropolis-Hastings move of one chain ---- *
  * The body of EXPLORE_MH_NOVARPAR's sweep for one (ivo, iwhich) (prjmh_temper_rf.f90:725-757):
  * PROPOSAL (:1386-1447, ENOS = 0: Cauchy step on voro(ivo,iwhich), |.| for the depth, then
@@ -513,7 +541,7 @@ double orc_loglhood_voro(int k, const double *node_depth, const double *node_vp,
  * prop_depth/prop_vp [k] (may be NULL) receive the proposal after INTERPLAYER_novar, *logL_prop
  * (may be NULL) its logL (untouched when outside).  Returns 1 accepted, 0 rejected, -1 rejected
  * because the proposal left the prior bounds (ioutside).                                     */
-int orc_mh_step(int k, double *node_depth, double *node_vp, double *logL,
+int orc_mh_step_chain(int chain, int k, double *node_depth, double *node_vp, double *logL,
                 int ivo, int iwhich, double cauchy, double u_acc, double beta, double sigma,
                 const double *prior,
                 const double *src_offset, const double *src_depth, int nsrc, const double *tobs,
@@ -552,7 +580,7 @@ int orc_mh_step(int k, double *node_depth, double *node_vp, double *logL,
     if (outside) {
         ret = -1;                                                /* :753-757 */
     } else {
-        const double ll = orc_loglhood_rt(k, v, d + 1, src_offset, src_depth, nsrc, tobs, sigma, NULL);
+        const double ll = chain_loglhood(chain, k, v, d + 1, src_offset, src_depth, nsrc, tobs, sigma);
         if (logL_prop) *logL_prop = ll;
         const double logPLratio = 0.0 + (ll - *logL) * beta;     /* :744-745, logPr = 0 (ENOS = 0) */
         if (u_acc >= exp(logPLratio)) {
@@ -579,7 +607,7 @@ int orc_mh_step(int k, double *node_depth, double *node_vp, double *logL,
  * 0 when pk is NULL (IPOIPR = 0).  CHECKBOUNDS (:1639-1678), LOGLHOOD, accept test (:689-699).
  * node_depth/node_vp have ldk slots; slots past k are zero and stay zero.
  * Returns 1 accepted, 0 rejected, -1 outside the bounds, 2 no birth/death proposed.        */
-int orc_bd_step(int *k_io, double *node_depth, double *node_vp, double *logL, int ldk,
+int orc_bd_step_chain(int chain, int *k_io, double *node_depth, double *node_vp, double *logL, int ldk,
                 double u_k, int idel, double u_z, double u_v, double u_acc, double beta,
                 double sigma, const double *prior, const double *pk, int kmin, int kmax,
                 const double *src_offset, const double *src_depth, int nsrc, const double *tobs,
@@ -635,7 +663,7 @@ int orc_bd_step(int *k_io, double *node_depth, double *node_vp, double *logL, in
     if (outside) {
         ret = -1;                                                /* :700-704 */
     } else {
-        const double ll = orc_loglhood_rt(kn, v, d + 1, src_offset, src_depth, nsrc, tobs, sigma, NULL);
+        const double ll = chain_loglhood(chain, kn, v, d + 1, src_offset, src_depth, nsrc, tobs, sigma);
         if (logL_prop) *logL_prop = ll;
         const double logPLratio = logPr + (ll - *logL) * beta;   /* :689-691 */
         if (u_acc >= exp(logPLratio)) {
@@ -664,7 +692,7 @@ void orc_bd_step_batch(int *k, double *voro, double *logL, int B, int ldk, const
     for (int b = 0; b < B; ++b) {
         double *row = voro + (size_t)b * 2 * ldk;
         double *pr = voro_prop ? voro_prop + (size_t)b * 2 * ldk : NULL;
-        accept[b] = orc_bd_step(&k[b], row, row + ldk, &logL[b], ldk, u_k[b], idel[b], u_z[b], u_v[b],
+        accept[b] = orc_bd_step_chain(b, &k[b], row, row + ldk, &logL[b], ldk, u_k[b], idel[b], u_z[b], u_v[b],
                                 u_acc[b], beta[b], sigma[b], prior, pk, kmin, kmax, src_offset,
                                 src_depth, nsrc, tobs, k_prop ? &k_prop[b] : NULL, pr,
                                 pr ? pr + ldk : NULL, logL_prop ? &logL_prop[b] : NULL);
@@ -676,7 +704,7 @@ void orc_bd_step_batch(int *k, double *voro, double *logL, int B, int ldk, const
  * maxlimsdRT]), LOGLHOOD (the travel times are recomputed: LOGLHOOD_RT ignores ipred), and
  * "reject iff ran_uni >= EXP((logL_new - logL)*beta_mh)".  sd_prior = { pertsdsdRT, minlimsdRT,
  * maxlimsdRT } (read_input.f90:237-241).  Returns 1 / 0 / -1 outside / 2 no move.            */
-int orc_sd_step(int k, const double *node_depth, const double *node_vp, double *logL, double *sigma,
+int orc_sd_step_chain(int chain, int k, const double *node_depth, const double *node_vp, double *logL, double *sigma,
                 double u_gate, double gauss, double u_acc, double beta, const double *sd_prior,
                 const double *src_offset, const double *src_depth, int nsrc, const double *tobs,
                 double *logL_prop)
@@ -684,8 +712,8 @@ int orc_sd_step(int k, const double *node_depth, const double *node_vp, double *
     if (!(u_gate >= 0.10)) return 2;                             /* :553-554 */
     const double snew = *sigma + sd_prior[0] * gauss;            /* :1630 */
     if ((snew - sd_prior[1]) < 0.0 || (sd_prior[2] - snew) < 0.0) return -1;   /* :1631-1632, :569-573 */
-    const double ll = orc_loglhood_rt(k, node_vp, node_depth + 1, src_offset, src_depth, nsrc, tobs,
-                                      snew, NULL);
+    const double ll = chain_loglhood(chain, k, node_vp, node_depth + 1, src_offset, src_depth, nsrc, tobs,
+                                     snew);
     if (logL_prop) *logL_prop = ll;
     const double logPLratio = (ll - *logL) * beta;               /* :560 */
     if (u_acc >= exp(logPLratio)) return 0;                      /* :562-564 */
@@ -703,7 +731,7 @@ void orc_sd_step_batch(const int *k, const double *voro, double *logL, double *s
 #pragma omp parallel for schedule(dynamic, 16)
     for (int b = 0; b < B; ++b) {
         const double *row = voro + (size_t)b * 2 * ldk;
-        accept[b] = orc_sd_step(k[b], row, row + ldk, &logL[b], &sigma[b], u_gate[b], gauss[b],
+        accept[b] = orc_sd_step_chain(b, k[b], row, row + ldk, &logL[b], &sigma[b], u_gate[b], gauss[b],
                                 u_acc[b], beta[b], sd_prior, src_offset, src_depth, nsrc, tobs,
                                 logL_prop ? &logL_prop[b] : NULL);
     }
@@ -780,7 +808,7 @@ void orc_mh_step_batch(const int *k, double *voro, double *logL, int B, int ldk,
     for (int b = 0; b < B; ++b) {
         double *row = voro + (size_t)b * 2 * ldk;
         double *pr = voro_prop ? voro_prop + (size_t)b * 2 * ldk : NULL;
-        accept[b] = orc_mh_step(k[b], row, row + ldk, &logL[b], ivo[b], iwhich[b], cauchy[b],
+        accept[b] = orc_mh_step_chain(b, k[b], row, row + ldk, &logL[b], ivo[b], iwhich[b], cauchy[b],
                                 u_acc[b], beta[b], sigma[b], prior, src_offset, src_depth, nsrc,
                                 tobs, pr, pr ? pr + ldk : NULL, logL_prop ? &logL_prop[b] : NULL);
     }

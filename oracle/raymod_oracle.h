@@ -103,10 +103,15 @@ double orc_loglhood_voro(int k, const double *node_depth, const double *node_vp,
                          const double *tobs, double sigma, double *tpred,
                          double *sorted_depth, double *sorted_vp);
 
+/* IAR = 1: register the chains' AR(1) state (idxarRT, arparRT per chain, armxRT) so that the moves
+ * below evaluate LOGLHOOD with the AR residual model (loglhood.f90:171-182); NULL = IAR = 0.  The
+ * `chain` argument of the single-chain moves indexes these arrays (-1: no AR). */
+void orc_set_chain_ar(const int *idxar, const double *arpar, double armx);
+
 /* "Next" rows N1 + N2: one fixed-dimension MH move of one chain -- PROPOSAL (ENOS = 0 Cauchy step,
  * prjmh_temper_rf.f90:1386-1447), INTERPLAYER_novar, CHECKBOUNDS2 (:1681-1716), LOGLHOOD and the
  * accept test of EXPLORE_MH_NOVARPAR (:739-757).  Random numbers are inputs.  See the .c file. */
-int orc_mh_step(int k, double *node_depth, double *node_vp, double *logL,
+int orc_mh_step_chain(int chain, int k, double *node_depth, double *node_vp, double *logL,
                 int ivo, int iwhich, double cauchy, double u_acc, double beta, double sigma,
                 const double *prior,
                 const double *src_offset, const double *src_depth, int nsrc, const double *tobs,
@@ -120,7 +125,7 @@ void orc_mh_step_batch(const int *k, double *voro, double *logL, int B, int ldk,
 /* N2: the birth/death move of EXPLORE_MH_NOVARPAR (:658-710): move choice, BIRTH_FULL (:997-1103) or
  * DEATH_FULL (:917-994), CHECKBOUNDS (:1639-1678), LOGLHOOD, accept with the Poisson-prior logPr.
  * Returns 1 accepted, 0 rejected, -1 outside, 2 no birth/death proposed.  See the .c file. */
-int orc_bd_step(int *k_io, double *node_depth, double *node_vp, double *logL, int ldk,
+int orc_bd_step_chain(int chain, int *k_io, double *node_depth, double *node_vp, double *logL, int ldk,
                 double u_k, int idel, double u_z, double u_v, double u_acc, double beta,
                 double sigma, const double *prior, const double *pk, int kmin, int kmax,
                 const double *src_offset, const double *src_depth, int nsrc, const double *tobs,
@@ -134,7 +139,7 @@ void orc_bd_step_batch(int *k, double *voro, double *logL, int B, int ldk, const
                        double *logL_prop);
 
 /* N2: the data-error move of EXPLORE_MH (:545-575) with PROPOSAL_SDRT (:1616-1635). */
-int orc_sd_step(int k, const double *node_depth, const double *node_vp, double *logL, double *sigma,
+int orc_sd_step_chain(int chain, int k, const double *node_depth, const double *node_vp, double *logL, double *sigma,
                 double u_gate, double gauss, double u_acc, double beta, const double *sd_prior,
                 const double *src_offset, const double *src_depth, int nsrc, const double *tobs,
                 double *logL_prop);

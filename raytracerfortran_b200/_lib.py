@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "libraytrace_b200
 # every symbol include/raytrace_b200.h declares
 EXPORTS = (
     "dff_", "dff7_", "tracerays_", "dff_batch", "loglhood_batch", "loglhood_batch_ar", "loglhood_batch_voro",
-    "rtb200_dff_batch_device", "rtb200_mh_step_device", "rtb200_mh_moves_device", "rtb200_bd_step_device", "rtb200_sd_step_device", "rtb200_ar_step_device",
+    "rtb200_dff_batch_device", "rtb200_mh_step_device", "rtb200_mh_moves_device", "rtb200_bd_step_device", "rtb200_sd_step_device", "rtb200_ar_step_device", "rtb200_set_chain_ar",
     "rtb200_init", "rtb200_shutdown", "rtb200_last_error", "rtb200_device_count",
     "rtb200_set_option", "rtb200_get_stat", "rtb200_fp64_peak_tflops", "rtb200_shard_range",
     "rtb200_selftest_fast_division",
@@ -64,6 +64,8 @@ def load():
     lib.rtb200_sd_step_device.argtypes = [vp, vp, vp, vp, i, i, vp, vp, vp, vp, dp, vp, vp, vp, i, vp, vp]
     lib.rtb200_ar_step_device.restype = i
     lib.rtb200_ar_step_device.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, dp, vp, vp, vp, i, vp, vp]
+    lib.rtb200_set_chain_ar.restype = i
+    lib.rtb200_set_chain_ar.argtypes = [vp, vp, d]
     lib.rtb200_init.restype = i
     lib.rtb200_init.argtypes = [i]
     lib.rtb200_shutdown.restype = None

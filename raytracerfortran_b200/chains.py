@@ -150,6 +150,16 @@ def sd_step_device(k, voro, logL, sigma, u_gate, gauss, u_acc, beta, sd_prior, s
     return accept
 
 
+def set_chain_ar(idxar=None, arpar=None, armx=0.5):
+    """IAR = 1: every likelihood evaluation of the move functions uses the chains' AR(1) state
+    (idxar [B] i32, arpar [B] f64 CUDA tensors, kept by reference: ar_step_device updates them in
+    place).  Call without arguments to return to IAR = 0 (rtb200_set_chain_ar)."""
+    if idxar is None:
+        _lib.check(_lib.load().rtb200_set_chain_ar(None, None, float(armx)))
+        return
+    _lib.check(_lib.load().rtb200_set_chain_ar(_ptr(idxar, torch.int32), _ptr(arpar, torch.float64), float(armx)))
+
+
 def ar_prior_array(minlimar=-0.5, maxlimar=0.9, pertarsdsc=10.0, armx=0.5):
     """pertarsdRT, minlimarRT, maxlimarRT, armxRT: read_input.f90:223-227 (pertarsdRT =
     (maxlimarRT - minlimarRT)/10) and rjmcmc_com.f90:93 (armxRT = 0.5)."""

@@ -63,6 +63,10 @@ struct Ctx {
     cudaGraphExec_t     mv_exec = nullptr;
     std::vector<size_t> mv_key;
     cudaStream_t        s_cap = nullptr;
+    // IAR = 1: the chains' AR(1) state, used by every likelihood evaluation of the move entries
+    const int    *chain_idxar = nullptr;
+    const double *chain_arpar = nullptr;
+    double        chain_armx  = 0.5;
     void  *pin = nullptr;          // pinned staging for small calls
     size_t pin_cap = 0;
     // options (<= 0: automatic)
@@ -712,6 +716,9 @@ BatchArgs move_eval_args(int B, int ldk, const double *d_src_offset, const doubl
     a.logc = log_norm_const(NSrc);
     a.padded = 1;
     a.sched = sched;
+    a.idxar = g.chain_idxar;         // IAR = 1 (rtb200_set_chain_ar); null otherwise
+    a.arpar = g.chain_arpar;
+    a.armx  = g.chain_armx;
     return a;
 }
 
@@ -782,7 +789,13 @@ int rtb200_mh_moves_device(const int *d_k, double *d_voro, double *d_logL, int B
                                (size_t)d_src_depth, (size_t)d_tobs, (size_t)NSrc, (size_t)d_accept,
                                (size_t)g.vels.p, (size_t)g.depths.p, (size_t)g.nl.p,
                                (size_t)g.vsorted.p, (size_t)g.mh_ll.p, (size_t)g.mh_out.p,
-                               (size_t)cfg.M, (size_t)cfg.grid, (size_t)cfg.variant, (size_t)g.opt_static_tiles};
+                               (size_t)cfg.M, (size_t)cfg.grid, (size_t)cfg.variant, (size_t)g.opt_static_tiles,
+                               (size_t)g.chain_idxar, (size_t)g.chain_arpar};
+    {
+        size_t bits;
+        memcpy(&bits, &g.chain_armx, sizeof bits);
+        key.push_back(bits);
+    }
     for (int i = 0; i < 7; ++i) {
         size_t bits;
         memcpy(&bits, &prior[i], sizeof bits);
@@ -904,6 +917,14 @@ int rtb200_sd_step_device(const int *d_k, const double *d_voro, double *d_logL, 
     return 0;
 }
 
+int rtb200_set_chain_ar(const int *d_idxar, const double *d_arpar, double armx) {
+    if ((d_idxar == nullptr) != (d_arpar == nullptr)) return fail("rtb200_set_chain_ar needs both arrays or neither");
+    g.chain_idxar = d_idxar;
+    g.chain_arpar = d_arpar;
+    g.chain_armx  = armx;
+    return 0;
+}
+
 int rtb200_ar_step_device(const int *d_k, const double *d_voro, double *d_logL,
                           const double *d_sigma, int *d_idxar, double *d_arpar, int B, int ldk,
                           const double *d_uchoice, const double *d_uprop, const double *d_gauss,
@@ -973,6 +994,8 @@ void rtb200_shutdown(void) {
     if (g.mv_exec) cudaGraphExecDestroy(g.mv_exec);
     g.mv_exec = nullptr;
     g.mv_key.clear();
+    g.chain_idxar = nullptr;
+    g.chain_arpar = nullptr;
     if (g.s_cap) cudaStreamDestroy(g.s_cap);
     g.s_cap = nullptr;
     cudaStreamDestroy(g.s_h2d);

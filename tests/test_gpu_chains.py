@@ -373,3 +373,65 @@ def test_ar_step_matches_oracle():
     fin = np.isfinite(cur_l) & (np.abs(cur_l) < 1e300)
     assert np.all(np.abs(got[fin] - cur_l[fin]) <= 1e-11 * np.maximum(np.abs(cur_l[fin]), nsrc * np.abs(np.log(sigma[fin]))))
     assert np.array_equal(got[~fin], cur_l[~fin])
+
+
+def test_all_moves_with_the_ar_likelihood():
+    """IAR = 1: with the chains' AR(1) state registered, every move (fixed-k, birth/death, sigma,
+    AR) evaluates the AR likelihood; six rounds of all four against the oracle."""
+    import torch
+    B, ldk, nsrc = 1500, 8, 20
+    k, voro, so, sd, tobs, sigma, _ = _setup(B, ldk, nsrc, 101)
+    rng = np.random.default_rng(102)
+    prior, sp, pk = chains.prior_array(), chains.sd_prior_array(), chains.poisson_pk(3.01, 1, ldk)
+    prior[:2] /= 10.0
+    ap = chains.ar_prior_array()
+    ap[3] = 5.0
+    beta = np.ones(B)
+    idxar = rng.integers(0, 2, B).astype(np.int32)
+    arpar = np.where(idxar == 1, rng.uniform(-0.5, 0.9, B), -1.5)
+    ll = np.empty(B)
+    for b in range(B):
+        pred = oracle.loglhood_rt(voro[b, 1, :k[b]], voro[b, 0, 1:k[b]], so, sd, tobs, sigma[b])[1]
+        ll[b] = oracle.loglhood_from_times_ar(pred, tobs, sigma[b], int(idxar[b]), float(arpar[b]), 5.0)
+    tk, tv, tl, tg, ti, ta, tb, ts, td, to = _dev(k, voro, ll, sigma, idxar, arpar, beta, so, sd, tobs)
+    chains.set_chain_ar(ti, ta, 5.0)
+    ck, cv, cl, cs, ci, ca = k.copy(), voro, ll, sigma, idxar, arpar
+    try:
+        for rnd in range(6):
+            oracle.set_chain_ar(ci, ca, 5.0)
+            u = rng.random((4, B))
+            idel = (2 + np.floor(rng.random(B) * np.maximum(ck - 1, 1))).astype(np.int32)
+            r = oracle.bd_step_batch(ck, cv, cl, u[0], idel, u[1], u[2], u[3], beta, cs, prior, pk, 1, ldk, so, sd, tobs)
+            t = _dev(u[0], idel, u[1], u[2], u[3])
+            acc = chains.bd_step_device(tk, tv, tl, t[0], t[1], t[2], t[3], t[4], tb, tg, prior, pk, 1, ldk, ts, td, to)
+            assert np.array_equal(acc.cpu().numpy(), r["accept"]), f"bd {rnd}"
+            ck, cv, cl = r["k"], r["voro"], r["logL"]
+            ivo = np.minimum(1 + rnd % 3, ck).astype(np.int32)
+            iwhich = np.full(B, 2, dtype=np.int32)
+            uu = rng.random((2, B))
+            cauchy = np.tan(np.pi * (uu[0] - 0.5))
+            r = oracle.mh_step_batch(ck, cv, cl, ivo, iwhich, cauchy, uu[1], beta, cs, prior, so, sd, tobs)
+            t = _dev(ivo, iwhich, cauchy, uu[1])
+            acc = chains.mh_step_device(tk, tv, tl, t[0], t[1], t[2], t[3], tb, tg, prior, ts, td, to)
+            assert np.array_equal(acc.cpu().numpy(), r["accept"]), f"mh {rnd}"
+            cv, cl = r["voro"], r["logL"]
+            us, gs = rng.random((2, B)), rng.standard_normal(B)
+            r = oracle.sd_step_batch(ck, cv, cl, cs, us[0], gs, us[1], beta, sp, so, sd, tobs)
+            t = _dev(us[0], gs, us[1])
+            acc = chains.sd_step_device(tk, tv, tl, tg, t[0], t[1], t[2], tb, sp, ts, td, to)
+            assert np.array_equal(acc.cpu().numpy(), r["accept"]), f"sd {rnd}"
+            cl, cs = r["logL"], r["sigma"]
+            ua, ga = rng.random((3, B)), rng.standard_normal(B)
+            r = oracle.ar_step_batch(ck, cv, cl, cs, ci, ca, ua[0], ua[1], ga, ua[2], beta, ap, so, sd, tobs)
+            t = _dev(ua[0], ua[1], ga, ua[2])
+            acc = chains.ar_step_device(tk, tv, tl, tg, ti, ta, t[0], t[1], t[2], t[3], tb, ap, ts, td, to)
+            assert np.array_equal(acc.cpu().numpy(), r["accept"]), f"ar {rnd}"
+            cl, ci, ca = r["logL"], r["idxar"], r["arpar"]
+        assert np.array_equal(tk.cpu().numpy(), ck)
+        assert np.array_equal(tv.cpu().numpy().view(np.uint64), cv.view(np.uint64))
+        assert np.array_equal(tg.cpu().numpy().view(np.uint64), cs.view(np.uint64))
+        assert np.array_equal(ti.cpu().numpy(), ci)
+        assert np.array_equal(ta.cpu().numpy().view(np.uint64), ca.view(np.uint64))
+    finally:
+        chains.set_chain_ar()
+        oracle.set_chain_ar()
