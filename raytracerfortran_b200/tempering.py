@@ -159,3 +159,37 @@ def tempering_swap_round_device(logL_local, beta_local, seed, round_index, group
     new[i] = torch.where(accept, beta[j], beta[i])
     new[j] = torch.where(accept, beta[i], beta[j])
     return new[rank * n_local:(rank + 1) * n_local].clone(), {"pairs_i": i, "pairs_j": j, "accept": accept}
+
+
+class LadderAdapter:
+    """The burn-in adaptation of the temperature ladder (prjmh_temper_rf.f90:363-383 with the
+    rolling window of TEMPSWP_MH, :1373-1379): swap proposals and acceptances are counted; once
+    more than `acceptance_window` proposals have been seen the acceptance rate is latched and the
+    counters reset; at that moment, during burn-in, dTlog grows by 2 % if the rate is below 0.2 and
+    shrinks by 2 % if it is above 0.5, and the betas are reassigned as 1/dTlog**(it-1).
+
+    `update(accept)` takes the accept mask of one swap round (any array-like of booleans) and
+    returns the new ladder (numpy array, T = 1 chains first) when it changed, else None."""
+
+    def __init__(self, n_replicas, dTlog, n_cold=1, acceptance_window=150):   # rjmcmc_com.f90:159
+        self.n, self.dTlog, self.n_cold = int(n_replicas), float(dTlog), int(n_cold)
+        self.window = int(acceptance_window)
+        self.ncswap = self.ncswapprop = 0
+        self.acceptance_rate = 0.25                         # :317
+
+    def update(self, accept, burn_in=True):
+        changed = False
+        for a in np.asarray(accept, dtype=bool).ravel():
+            self.ncswap += int(a)
+            self.ncswapprop += 1
+            if self.ncswapprop > self.window:               # :1375-1379
+                self.acceptance_rate = self.ncswap / self.ncswapprop
+                self.ncswap = self.ncswapprop = 0
+                if burn_in:                                 # :363-372
+                    if self.acceptance_rate < 0.2:
+                        self.dTlog *= 1.02
+                        changed = True
+                    if self.acceptance_rate > 0.5:
+                        self.dTlog *= 0.98
+                        changed = True
+        return temperature_ladder(self.n, self.dTlog, self.n_cold) if changed else None

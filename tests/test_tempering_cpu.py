@@ -132,3 +132,21 @@ def test_mh_accept_rule_matches_explore_mh_novarpar():
         want = (not bool(out[i])) and not (float(u[i]) >= math.exp(float(lpr[i]) + (float(new[i]) - float(cur[i])) * float(beta[i])))
         assert bool(acc[i]) == want
     assert 0.2 < acc.double().mean() < 0.9
+
+
+def test_ladder_adapter_follows_the_burn_in_rule():
+    """prjmh_temper_rf.f90:363-383, :1373-1379: rate latched after more than `window` proposals;
+    dTlog * 1.02 below 0.2, * 0.98 above 0.5, untouched in between or after burn-in."""
+    ad = tempering.LadderAdapter(6, 1.4, acceptance_window=10)
+    assert ad.update(np.zeros(10, bool)) is None and ad.acceptance_rate == 0.25      # window not exceeded yet
+    lad = ad.update(np.zeros(1, bool))                                               # 11th proposal: rate 0
+    assert ad.acceptance_rate == 0.0 and abs(ad.dTlog - 1.4 * 1.02) < 1e-15
+    assert np.allclose(lad, 1.0 / (1.4 * 1.02) ** np.arange(6)) and (ad.ncswap, ad.ncswapprop) == (0, 0)
+    lad = ad.update(np.ones(11, bool))                                               # rate 1 -> shrink
+    assert ad.acceptance_rate == 1.0 and abs(ad.dTlog - 1.4 * 1.02 * 0.98) < 1e-15 and lad is not None
+    acc = np.zeros(11, bool)
+    acc[:4] = True                                                                   # 4/11 = 0.36: keep
+    d = ad.dTlog
+    assert ad.update(acc) is None and ad.dTlog == d and abs(ad.acceptance_rate - 4 / 11) < 1e-15
+    assert ad.update(np.zeros(11, bool), burn_in=False) is None and ad.dTlog == d    # after burn-in: only the rate
+    assert ad.acceptance_rate == 0.0
