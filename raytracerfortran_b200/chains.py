@@ -270,13 +270,27 @@ def mh_moves_device(k, voro, logL, pos, n_moves, beta, sigma, prior, src_offset,
 
 
 def mcmc_step_device(k, voro, logL, sigma, beta, prior, sd_prior, pk, kmin, kmax, src_offset,
-                     src_depth, tobs, generator=None):
+                     src_depth, tobs, generator=None, ar=None):
     """One iteration of the sampler's worker loop (prjmh_temper_rf.f90:421-447) for every chain:
     EXPLORE_MH_NOVARPAR -- the birth/death move, then the sweep over ivo = 1..k, iwhich = 1, 2 --
     followed by EXPLORE_MH's data-error move.  All chains step together; a chain with fewer than
     ivo nodes sits that move out, exactly as its own loop would have ended.  Everything stays on
-    the device; random numbers come from `generator`.  Returns a dict of per-chain counts
-    (device tensors): accepted / proposed fixed-k moves, birth/death and sigma outcomes."""
+    the device; random numbers come from `generator`.  With `ar = (idxar, arpar, ar_prior)` the
+    sampler's IAR = 1 mode is run: every move evaluates the AR(1) likelihood of the chain's state and
+    EXPLORE_MH's AR move follows the data-error move (:583-631).  Returns a dict of per-chain
+    counts (device tensors): accepted / proposed fixed-k moves, birth/death, sigma and AR outcomes."""
+    if ar is not None:
+        set_chain_ar(ar[0], ar[1], float(np.asarray(ar[2], dtype=np.float64)[3]))
+    try:
+        return _mcmc_step(k, voro, logL, sigma, beta, prior, sd_prior, pk, kmin, kmax, src_offset, src_depth,
+                          tobs, generator, ar)
+    finally:
+        if ar is not None:
+            set_chain_ar()
+
+
+def _mcmc_step(k, voro, logL, sigma, beta, prior, sd_prior, pk, kmin, kmax, src_offset, src_depth, tobs,
+               generator, ar):
     dev = voro.device
     B, _, ldk = voro.shape
     f64 = torch.float64
@@ -304,5 +318,11 @@ def mcmc_step_device(k, voro, logL, sigma, beta, prior, sd_prior, pk, kmin, kmax
     gauss = torch.randn(B, dtype=f64, device=dev, generator=generator)
     sd = sd_step_device(k, voro, logL, sigma, us[0].contiguous(), gauss, us[1].contiguous(), beta,
                         sd_prior, src_offset, src_depth, tobs)
-    return {"accepted": (accept[:m] == 1).sum(dim=0), "proposed": 2 * k.to(torch.int64) - 1,
-            "bd": bd, "sd": sd}
+    out = {"accepted": (accept[:m] == 1).sum(dim=0), "proposed": 2 * k.to(torch.int64) - 1,
+           "bd": bd, "sd": sd}
+    if ar is not None:
+        ua = torch.rand((3, B), dtype=f64, device=dev, generator=generator)
+        ga = torch.randn(B, dtype=f64, device=dev, generator=generator)
+        out["ar"] = ar_step_device(k, voro, logL, sigma, ar[0], ar[1], ua[0].contiguous(), ua[1].contiguous(), ga,
+                                   ua[2].contiguous(), beta, ar[2], src_offset, src_depth, tobs)
+    return out

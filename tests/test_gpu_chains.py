@@ -435,3 +435,36 @@ def test_all_moves_with_the_ar_likelihood():
     finally:
         chains.set_chain_ar()
         oracle.set_chain_ar()
+
+
+def test_mcmc_step_device_with_ar():
+    """IAR = 1 through mcmc_step_device: after a few iterations the stored logL is the AR(1)
+    likelihood of the stored (model, sigma, idxar, arpar), and AR parameters stay inside the prior."""
+    import torch
+    B, ldk, nsrc = 300, 8, 20
+    k, voro, so, sd, tobs, sigma, _ = _setup(B, ldk, nsrc, 111)
+    rng = np.random.default_rng(112)
+    idxar = np.zeros(B, dtype=np.int32)
+    arpar = np.full(B, -1.5)
+    ll = np.array([oracle.loglhood_rt(voro[b, 1, :k[b]], voro[b, 0, 1:k[b]], so, sd, tobs, sigma[b])[0]
+                   for b in range(B)])
+    ap = chains.ar_prior_array()
+    tk, tv, tl, tg, ti, ta, tb, ts, td, to = _dev(k, voro, ll, sigma, idxar, arpar, np.ones(B), so, sd, tobs)
+    prior, sp, pk = chains.prior_array(), chains.sd_prior_array(), chains.poisson_pk(3.01, 1, ldk)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    seen = set()
+    for it in range(6):
+        r = chains.mcmc_step_device(tk, tv, tl, tg, tb, prior, sp, pk, 1, ldk, ts, td, to, generator=gen,
+                                    ar=(ti, ta, ap))
+        seen |= set(np.unique(r["ar"].cpu().numpy()).tolist())
+    assert {0, 1} <= seen <= {-1, 0, 1}
+    kk, vv, sg, ii, aa, got = (t.cpu().numpy() for t in (tk, tv, tg, ti, ta, tl))
+    assert ii.max() == 1 and np.all((aa[ii == 1] >= -0.5) & (aa[ii == 1] <= 0.9)) and np.all(aa[ii == 0] == -1.5)
+    for b in range(0, B, 7):
+        n = int(kk[b])
+        pred = oracle.loglhood_rt(vv[b, 1, :n], vv[b, 0, 1:n], so, sd, tobs, sg[b])[1]
+        ref = oracle.loglhood_from_times_ar(pred, tobs, sg[b], int(ii[b]), float(aa[b]), 0.5)
+        if abs(ref) < 1e300:
+            assert abs(got[b] - ref) <= 1e-11 * max(abs(ref), nsrc * abs(np.log(sg[b])))
+        else:
+            assert got[b] == ref
