@@ -50,7 +50,7 @@ struct TileCfg {
     int TS;       // row stride of the travel-time tile (odd)
     int threads;  // CTA size
     int grid;     // persistent CTAs
-    int variant;  // 0: lock-step loops, 1: lane state machine with refill
+    int variant;  // 0: plain per-thread loops, 1: lane state machine with refill, 3: the same for deep models
     int use_tma;  // rows are 16-byte aligned: stage with cp.async.bulk
     int logl_shuffle;  // reduce the residuals with warp shuffles (tree order) instead of source order
     size_t smem;  // dynamic shared memory bytes
