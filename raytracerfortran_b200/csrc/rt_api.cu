@@ -355,11 +355,18 @@ int run_host(const HostCall &h) {
     const int ncomp = g.opt_comp_streams == 1 ? 1 : 2;
     chunk = std::max(chunk, (B + kMaxChunks - 1) / kMaxChunks);
     chunk = (chunk + cfg.M - 1) / cfg.M * cfg.M;
-    const int nchunks = (int)((B + chunk - 1) / chunk);
+    // The first chunk is short (one wave when the default chunking is in force) so that the GPU
+    // starts after a quarter of the copy time a full chunk would take; `lead` is its size.
+    size_t lead = chunk;
+    if (g.opt_chunk_models <= 0 && wave >= (size_t)cfg.M && wave < chunk && B > 2 * chunk &&
+        (B - wave + chunk - 1) / chunk + 1 <= (size_t)kMaxChunks)
+        lead = wave;
+    const int nchunks = (int)(1 + (B > lead ? (B - lead + chunk - 1) / chunk : 0));
 
     const double logc = h.logL ? log_norm_const(h.nsrc) : 0.0;
     for (int j = 0; j < nchunks; ++j) {
-        const size_t j0 = (size_t)j * chunk, j1 = std::min(B, j0 + chunk), nb = j1 - j0;
+        const size_t j0 = j == 0 ? 0 : lead + (size_t)(j - 1) * chunk;
+        const size_t j1 = std::min(B, j == 0 ? lead : j0 + chunk), nb = j1 - j0;
         CK(cudaMemcpyAsync(g.vels.as<double>() + j0 * h.ldv, h.vels + j0 * h.ldv, nb * h.ldv * 8,
                            cudaMemcpyHostToDevice, g.s_h2d));
         if (ldz > 0)
