@@ -42,6 +42,16 @@ def test_library_is_sm100a_only(lib):
     assert archs == {"sm_100a"}, archs
 
 
+def test_kernels_stage_tiles_with_tma_bulk_copies(lib):
+    """The batch kernels bring a tile's rows in with cp.async.bulk + mbarrier: the SASS carries
+    UBLKCP (the bulk copy) and SYNCS (mbarrier arrive/wait), and fp64 math only (no tensor-core
+    instructions: the path is not a contraction)."""
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert sass.count("UBLKCP") >= 3 and sass.count("SYNCS") >= 3          # one per kernel variant at least
+    assert "DFMA" in sass and "MUFU.RSQ64H" in sass
+    assert not re.search(r"\b(HMMA|IMMA|UTCHMMA|UTCMMA|HGMMA)\b", sass)
+
+
 def test_shard_range_partitions_the_model_axis(lib):
     for B in (0, 1, 7, 64, 1_000_003):
         for world in (1, 2, 3, 8):
