@@ -124,3 +124,25 @@ def test_fortran_shim_binds_only_exported_symbols():
     names = set(re.findall(r'bind\(C,\s*name="([A-Za-z0-9_]+)"\)', src))
     assert {"tracerays_", "dff_batch", "loglhood_batch"} <= names
     assert names <= set(_lib.EXPORTS), names - set(_lib.EXPORTS)
+
+
+def test_header_is_plain_c_and_a_c_caller_links(tmp_path):
+    """include/raytrace_b200.h is valid C99 and C++ (extern "C", plain pointers), and a C program
+    written against it links with the library; without a GPU it fails loudly, never silently."""
+    hdr = os.path.join(ROOT, "include", "raytrace_b200.h")
+    cc, cxx = "/usr/bin/gcc", "/usr/bin/g++"
+    if not (os.path.exists(cc) and os.path.exists(cxx)):
+        pytest.skip("no host compiler")
+    assert subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr]).returncode == 0
+    assert subprocess.run([cxx, "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr]).returncode == 0
+    exe = str(tmp_path / "dff_batch_example")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", os.path.join(ROOT, "examples", "dff_batch_example.c"),
+                        "-I" + os.path.join(ROOT, "include"), "-L" + libdir, "-lraytrace_b200",
+                        "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if run.returncode == 0:
+        assert "logL" in run.stdout                      # a GPU was there
+    else:
+        assert "no usable CUDA device" in run.stderr or "sm_100a" in run.stderr
