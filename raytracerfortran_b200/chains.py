@@ -10,6 +10,7 @@ sigma [B].  torch supplies the tensors, the stream and the random numbers; the m
 library's kernels.  The birth/death move (BIRTH_FULL /
 DEATH_FULL, :658-710) is `bd_step_device`, the data-error move of EXPLORE_MH (:545-575) `sd_step_device`, its AR(1) move (:583-631) `ar_step_device`.
 """
+import ctypes as C
 import math
 
 import numpy as np
@@ -60,7 +61,6 @@ def mh_step_device(k, voro, logL, ivo, iwhich, cauchy, u_acc, beta, sigma, prior
     if pr.size != 7:
         raise ValueError("prior must hold 7 doubles (see prior_array)")
     st = stream if stream is not None else torch.cuda.current_stream(dev)
-    import ctypes as C
     rc = _lib.load().rtb200_mh_step_device(
         _ptr(k, i32), _ptr(voro, f64), _ptr(logL, f64), B, ldk, _ptr(ivo, i32), _ptr(iwhich, i32),
         _ptr(cauchy, f64), _ptr(u_acc, f64), _ptr(beta, f64), _ptr(sigma, f64),
@@ -98,7 +98,6 @@ def bd_step_device(k, voro, logL, u_k, idel, u_z, u_v, u_acc, beta, sigma, prior
     pr = np.ascontiguousarray(prior, dtype=np.float64)
     if pr.size != 7:
         raise ValueError("prior must hold 7 doubles (see prior_array)")
-    import ctypes as C
     dp = C.POINTER(C.c_double)
     pkp = None
     if pk is not None:
@@ -139,7 +138,6 @@ def sd_step_device(k, voro, logL, sigma, u_gate, gauss, u_acc, beta, sd_prior, s
     sp = np.ascontiguousarray(sd_prior, dtype=np.float64)
     if sp.size != 3:
         raise ValueError("sd_prior must hold 3 doubles (see sd_prior_array)")
-    import ctypes as C
     st = stream if stream is not None else torch.cuda.current_stream(dev)
     rc = _lib.load().rtb200_sd_step_device(
         _ptr(k, i32), _ptr(voro, f64), _ptr(logL, f64), _ptr(sigma, f64), B, ldk, _ptr(u_gate, f64),
@@ -182,7 +180,6 @@ def ar_step_device(k, voro, logL, sigma, idxar, arpar, u_choice, u_prop, gauss, 
     ap = np.ascontiguousarray(ar_prior, dtype=np.float64)
     if ap.size != 4:
         raise ValueError("ar_prior must hold 4 doubles (see ar_prior_array)")
-    import ctypes as C
     st = stream if stream is not None else torch.cuda.current_stream(dev)
     rc = _lib.load().rtb200_ar_step_device(
         _ptr(k, i32), _ptr(voro, f64), _ptr(logL, f64), _ptr(sigma, f64), _ptr(idxar, i32),
@@ -256,7 +253,6 @@ def mh_moves_device(k, voro, logL, pos, n_moves, beta, sigma, prior, src_offset,
     pr = np.ascontiguousarray(prior, dtype=np.float64)
     if pr.size != 7:
         raise ValueError("prior must hold 7 doubles (see prior_array)")
-    import ctypes as C
     st = torch.cuda.current_stream(dev)
     rc = _lib.load().rtb200_mh_moves_device(
         _ptr(k, i32), _ptr(voro, f64), _ptr(logL, f64), B, ldk, int(n_moves), _ptr(buf["ivo"], i32),
