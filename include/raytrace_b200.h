@@ -57,6 +57,21 @@ void tracerays_(const double *vels, const double *depths, const int *NLayers,
                 const double *src_offset, const double *src_depth, const int *NSrc,
                 double *timeP, const int *keep_delta);
 
+/* The same entry under the names Fortran compilers give  module raymod :: TraceRays  (gfortran,
+ * ifort/ifx, nvfortran/PGI), so that objects already compiled against the reference's raymod.mod
+ * (ray_tracing_sampling/loglhood.f90 calls TraceRays at :135,144) link against this library as
+ * they are; the checked-in raymod.mod is gfortran's.  Explicit-shape dummy arrays are passed as
+ * plain pointers and scalars by reference: exactly tracerays_'s ABI. */
+void __raymod_MOD_tracerays(const double *vels, const double *depths, const int *NLayers,
+                            const double *src_offset, const double *src_depth, const int *NSrc,
+                            double *timeP, const int *keep_delta);
+void raymod_mp_tracerays_(const double *vels, const double *depths, const int *NLayers,
+                          const double *src_offset, const double *src_depth, const int *NSrc,
+                          double *timeP, const int *keep_delta);
+void raymod_tracerays_(const double *vels, const double *depths, const int *NLayers,
+                       const double *src_offset, const double *src_depth, const int *NSrc,
+                       double *timeP, const int *keep_delta);
+
 /* ------------------------------------------------------------------------------------------
  * Batched entries (new; the reference evaluates one model per call)
  * ---------------------------------------------------------------------------------------- */

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "libraytrace_b200
 
 # every symbol include/raytrace_b200.h declares
 EXPORTS = (
-    "dff_", "dff7_", "tracerays_", "dff_batch", "loglhood_batch", "loglhood_batch_ar", "loglhood_batch_voro",
+    "dff_", "dff7_", "tracerays_", "__raymod_MOD_tracerays", "raymod_mp_tracerays_", "raymod_tracerays_", "dff_batch", "loglhood_batch", "loglhood_batch_ar", "loglhood_batch_voro",
     "rtb200_dff_batch_device", "rtb200_mh_step_device", "rtb200_mh_moves_device", "rtb200_bd_step_device", "rtb200_sd_step_device", "rtb200_ar_step_device", "rtb200_set_chain_ar",
     "rtb200_init", "rtb200_shutdown", "rtb200_last_error", "rtb200_device_count",
     "rtb200_set_option", "rtb200_get_stat", "rtb200_fp64_peak_tflops", "rtb200_shard_range",
@@ -41,6 +41,9 @@ def load():
     lib.dff_.argtypes = [dp, dp, ip, dp, dp, ip, dp, ip]
     lib.tracerays_.restype = None
     lib.tracerays_.argtypes = [dp, dp, ip, dp, dp, ip, dp, ip]
+    for alias in ("__raymod_MOD_tracerays", "raymod_mp_tracerays_", "raymod_tracerays_"):
+        getattr(lib, alias).restype = None
+        getattr(lib, alias).argtypes = [dp, dp, ip, dp, dp, ip, dp, ip]
     lib.dff7_.restype = None
     lib.dff7_.argtypes = [dp, dp, ip, dp, dp, ip, dp]
     lib.dff_batch.restype = i

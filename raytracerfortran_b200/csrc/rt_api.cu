@@ -556,6 +556,20 @@ void tracerays_(const double *vels, const double *depths, const int *NLayers,
              keep_delta ? *keep_delta : -1);
 }
 
+// module raymod's TraceRays under the names Fortran compilers give a module procedure, so objects
+// compiled against the reference's raymod.mod (loglhood.o) link without the shim: explicit-shape
+// arrays are plain pointers and scalars go by reference, the same ABI as tracerays_.
+#define RTB200_TRACERAYS_ALIAS(name)                                                        \
+    void name(const double *vels, const double *depths, const int *NLayers,                 \
+              const double *src_offset, const double *src_depth, const int *NSrc,           \
+              double *timeP, const int *keep_delta) {                                       \
+        tracerays_(vels, depths, NLayers, src_offset, src_depth, NSrc, timeP, keep_delta);  \
+    }
+RTB200_TRACERAYS_ALIAS(__raymod_MOD_tracerays)   // gfortran
+RTB200_TRACERAYS_ALIAS(raymod_mp_tracerays_)     // ifort / ifx
+RTB200_TRACERAYS_ALIAS(raymod_tracerays_)        // nvfortran / PGI (the compiler of the shipped binary)
+#undef RTB200_TRACERAYS_ALIAS
+
 int dff_batch(const double *vels, const double *depths, const int *nlayers, const int *B,
               const int *ldv, const int *ldz, const double *src_offset, const double *src_depth,
               const int *NSrc, double *timeP, const double *tobs, const double *sigma,

@@ -52,13 +52,15 @@ def dff7(vels, depths, src_offset, src_depth):
     return t
 
 
-def TraceRays(vels, depths, NLayers, src_offset, src_depth, NSrc, keep_delta=-1):
+def TraceRays(vels, depths, NLayers, src_offset, src_depth, NSrc, keep_delta=-1, symbol="tracerays_"):
     """CALL TraceRays(vels, depths, NLayers, src_offset, src_depth, NSrc, timeP, keep_delta)
-    (subroutineR-quiet.f90:467; call sites loglhood.f90:135,144).  Returns timeP."""
+    (subroutineR-quiet.f90:467; call sites loglhood.f90:135,144).  Returns timeP.  `symbol` picks
+    the exported name: tracerays_ (the shim's) or a compiler-mangled module-procedure name
+    (__raymod_MOD_tracerays, raymod_mp_tracerays_, raymod_tracerays_)."""
     v, z, so, sd = _d(vels), _d(depths), _d(src_offset), _d(src_depth)
     t = np.zeros(int(NSrc))
-    _lib.load().tracerays_(_p(v), _p(z), _ci(NLayers), _p(so), _p(sd), _ci(NSrc), _p(t),
-                           _ci(keep_delta))
+    getattr(_lib.load(), symbol)(_p(v), _p(z), _ci(NLayers), _p(so), _p(sd), _ci(NSrc), _p(t),
+                                 _ci(keep_delta))
     _lib.check()
     return t
 

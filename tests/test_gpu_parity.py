@@ -246,6 +246,18 @@ def test_more_models_per_tile_than_threads(variant):
             assert rt.get_stat("tile_models") > rt.get_stat("threads")
 
 
+def test_tracerays_under_the_compilers_module_procedure_names(golden):
+    """Objects compiled against the reference's raymod.mod call __raymod_MOD_tracerays (gfortran),
+    raymod_mp_tracerays_ (ifort) or raymod_tracerays_ (nvfortran): same entry, same bits."""
+    c = golden["config1"]
+    so, sd = np.array(c["src_offset_full"]), np.array(c["src_depth_full"])
+    want = rt.TraceRays(c["vels"], c["depths"], len(c["depths"]), so, sd, len(so))
+    ref, _, _ = oracle.trace_rays(c["vels"], c["depths"], so, sd)
+    assert_bitexact(want, ref, "tracerays_")
+    for name in ("__raymod_MOD_tracerays", "raymod_mp_tracerays_", "raymod_tracerays_"):
+        assert_bitexact(rt.TraceRays(c["vels"], c["depths"], len(c["depths"]), so, sd, len(so), symbol=name), ref, name)
+
+
 def test_empty_and_single():
     v, z, nl = workloads.make_models(1, 6, 1)
     so, sd = workloads.make_sources(1, 1)
