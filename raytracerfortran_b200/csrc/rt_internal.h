@@ -42,6 +42,16 @@ struct BatchArgs {
     int          *sched;
 };
 
+// Variant 4's shared-memory geometry, precomputed by the host (launch_batch) so that the kernel
+// reads every offset as a constant-bank operand: byte offsets from the dynamic smem base.
+struct QGeom {
+    uint32_t tab, src, T, q, st, ctr;    // tables, sources, travel-time slots, ray queues, ray state, counters
+    uint32_t rowB, lp8;                  // bytes per model row of the tables, per sub-table
+    uint32_t oHV, oZ, oVV, oIVM;         // sub-table offsets inside a model row
+    uint32_t oD;                         // source depths after the offsets
+    uint32_t qbytes;                     // bytes per queue buffer
+};
+
 // Tile geometry chosen by the host for one launch.
 struct TileCfg {
     int M;        // models per tile (even)
@@ -54,6 +64,7 @@ struct TileCfg {
     int use_tma;  // rows are 16-byte aligned: stage with cp.async.bulk
     int logl_shuffle;  // reduce the residuals with warp shuffles (tree order) instead of source order
     size_t smem;  // dynamic shared memory bytes
+    QGeom  q;     // filled in by launch_batch
 };
 
 // Prior and proposal scales of the fixed-dimension MH move (read_input.f90:207-214).

@@ -98,7 +98,7 @@ def test_readme_example(golden):
 # ---------------------------------------------------------------------------------------------
 # batched sweeps against the oracle, both kernel variants
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4])
 @pytest.mark.parametrize("B,nlayers,nsrc,seed", [(1500, 10, 64, 2), (257, 4, 20, 11), (64, 29, 256, 3),
                                                  (33, 1, 7, 5)])
 def test_dff_batch_bitexact(variant, B, nlayers, nsrc, seed):
@@ -115,7 +115,7 @@ def test_dff_batch_bitexact(variant, B, nlayers, nsrc, seed):
     assert rt.get_stat("variant") == variant
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4])
 def test_near_critical_50_layers(variant):
     """config-5 style rays: p*v -> 1, ~99 % bisection, Newton clamps."""
     rt.set_option("variant", variant)
@@ -183,7 +183,7 @@ def test_edge_geometry():
     assert [oracle.which_layer(z[0], d) for d in sd[:5]] == [1, 2, 3, 3, 4]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4])
 def test_ragged_batches_and_chunking(variant):
     rt.set_option("variant", variant)
     rng = np.random.default_rng(77)
@@ -204,7 +204,7 @@ def test_ragged_batches_and_chunking(variant):
         assert_logl_close(got["logL"], ref["logL"], nsrc, sigma)
 
 
-@pytest.mark.parametrize("variant", [1, 3])
+@pytest.mark.parametrize("variant", [1, 3, 4])
 def test_tile_scheduling_and_host_pipeline_options(variant):
     """Many more tiles than persistent CTAs: tiles claimed from the global counter (repeated
     launches reuse counter slots the kernel must leave zeroed), the static stride, and the host
@@ -227,7 +227,7 @@ def test_tile_scheduling_and_host_pipeline_options(variant):
     assert rt.get_stat("grid") < B // 8          # the tiles did outnumber the CTAs
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 4])
 def test_more_models_per_tile_than_threads(variant):
     """Few sources and shallow models let a tile hold more models than the CTA has threads."""
     rt.set_option("variant", variant)
