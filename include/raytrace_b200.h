@@ -163,6 +163,15 @@ int rtb200_mh_step_device(const int *d_k, double *d_voro, double *d_logL, int B,
                           const double *prior, const double *d_src_offset,
                           const double *d_src_depth, const double *d_tobs, int NSrc,
                           int *d_accept, void *stream);
+/* The same move with the accept test ordered behind a CUDA event (cudaEvent_t, may be NULL): the
+ * proposal and likelihood kernels do not read d_beta, so a tempering swap round that is still
+ * rewriting the betas on another stream (rtb200_swap_round_device) overlaps with them. */
+int rtb200_mh_step_device_ev(const int *d_k, double *d_voro, double *d_logL, int B, int ldk,
+                          const int *d_ivo, const int *d_iwhich, const double *d_cauchy,
+                          const double *d_uacc, const double *d_beta, const double *d_sigma,
+                          const double *prior, const double *d_src_offset,
+                          const double *d_src_depth, const double *d_tobs, int NSrc,
+                          int *d_accept, void *stream, void *beta_ready_event);
 
 /* n_moves consecutive calls of rtb200_mh_step_device in one: move m uses row m of d_ivo, d_iwhich,
  * d_cauchy, d_uacc and writes row m of d_accept (all [n_moves][B]).  The run is captured once into
@@ -233,6 +242,25 @@ int rtb200_ar_step_device(const int *d_k, const double *d_voro, double *d_logL,
                           const double *d_src_offset, const double *d_src_depth,
                           const double *d_tobs, int NSrc, int *d_accept, void *stream);
 
+/* The parallel-tempering swap round (TEMPSWP_MH, prjmh_temper_rf.f90:1329-1384; master loop
+ * :326-349) for n chains spread over the ranks of one job, decisions taken on the device.
+ * Every rank calls rtb200_swap_pack_device on its own chains (d_out[i] = (logL[i], beta[i])),
+ * all-gathers the packed pairs in rank order (the path's only collective: 16 bytes per chain),
+ * and calls rtb200_swap_round_device on the gathered array: the round's pairing (a keyed
+ * bijection of [0, n); pair t = (perm(2t), perm(2t+1))) and its uniforms are functions of
+ * (seed, round) alone, so all ranks take identical decisions; chain pair (i, j) is accepted iff
+ * u <= EXP((beta_j - beta_i)*(logL_i - logL_j)) (:1339-1342) and exchanges betas (the reference
+ * exchanges the states and keeps the temperatures in place, :1351-1357: the same Markov kernel).
+ *   d_all [n][2] gathered (logL, beta);  this rank owns chains [lo, lo + n_local)
+ *   d_beta_local [n_local] out: the betas of this rank's chains after the round
+ *   d_accept [n/2] out or NULL: 1/0 per pair;  d_partner [n_local] out or NULL: the partner's
+ *   global index when the swap was accepted, -1 - index when rejected, -1 when unpaired (odd n) */
+int rtb200_swap_pack_device(const double *d_logL, const double *d_beta, int n, double *d_out,
+                            void *stream);
+int rtb200_swap_round_device(const double *d_all, int n, int lo, int n_local,
+                             unsigned long long seed, unsigned long long round,
+                             double *d_beta_local, int *d_accept, int *d_partner, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Runtime control and introspection
  * ---------------------------------------------------------------------------------------- */
@@ -246,7 +274,9 @@ int         rtb200_device_count(void);        /* 0 without a driver / device    
  *          consecutive chunks alternate between two so one chunk's tail overlaps the next);
  *          "static_tiles" (1: CTAs stride over the tiles instead of claiming them from a counter);
  *          "logl_shuffle" (1: reduce the residuals of a model with a warp-shuffle tree instead of
- *          the reference's source order -- same terms, ~N ulp from the ordered sum; default 0) */
+ *          the reference's source order -- same terms, ~N ulp from the ordered sum; default 0);
+ *          "stage_pageable" (-1 default: large pageable host inputs are copied by a few host
+ *          threads into a pinned ring so that H2D stays asynchronous; 0 never; 1 always) */
 int         rtb200_set_option(const char *name, double value);
 /* stats of the last batched call: "kernel_ms", "total_ms", "launches" (cumulative),
  *          "tile_models", "tile_sources", "smem_bytes", "grid", "threads", "ctas_per_sm" */

@@ -40,13 +40,16 @@ def cauchy_deviates(u):
 
 
 def mh_step_device(k, voro, logL, ivo, iwhich, cauchy, u_acc, beta, sigma, prior,
-                   src_offset, src_depth, tobs, accept=None, stream=None):
+                   src_offset, src_depth, tobs, accept=None, stream=None, beta_ready=None):
     """One move of every chain, in place on `voro` and `logL`.
 
     k [B] i32, voro [B, 2, ldk] f64, logL/beta/sigma/cauchy/u_acc [B] f64, ivo/iwhich [B] i32
     (1-based node, 1 = depth / 2 = vp), src_offset/src_depth/tobs [NSrc] f64: CUDA tensors.
     prior: 7 doubles on the host (prior_array).  Asynchronous on `stream` (default: torch's
-    current stream).  Returns accept [B] i32: 1 accepted, 0 rejected, -1 outside the bounds."""
+    current stream).  `beta_ready` (a torch.cuda.Event, e.g. SwapRound.done) orders only the
+    accept test behind it, so a swap round still running on another stream overlaps with the
+    proposal and likelihood kernels.  Returns accept [B] i32: 1 accepted, 0 rejected, -1 outside
+    the bounds."""
     if not voro.is_cuda:
         raise ValueError("mh_step_device needs CUDA tensors (there is no CPU path)")
     dev = voro.device
@@ -61,12 +64,13 @@ def mh_step_device(k, voro, logL, ivo, iwhich, cauchy, u_acc, beta, sigma, prior
     if pr.size != 7:
         raise ValueError("prior must hold 7 doubles (see prior_array)")
     st = stream if stream is not None else torch.cuda.current_stream(dev)
-    rc = _lib.load().rtb200_mh_step_device(
+    rc = _lib.load().rtb200_mh_step_device_ev(
         _ptr(k, i32), _ptr(voro, f64), _ptr(logL, f64), B, ldk, _ptr(ivo, i32), _ptr(iwhich, i32),
         _ptr(cauchy, f64), _ptr(u_acc, f64), _ptr(beta, f64), _ptr(sigma, f64),
         pr.ctypes.data_as(C.POINTER(C.c_double)), _ptr(src_offset, f64), _ptr(src_depth, f64),
         _ptr(tobs, f64), src_offset.numel(), _ptr(accept, i32),
-        st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle())
+        st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle(),
+        beta_ready.cuda_event if beta_ready is not None else None)
     _lib.check(rc)
     return accept
 

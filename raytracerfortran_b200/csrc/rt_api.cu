@@ -15,7 +15,11 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 namespace {
 
@@ -57,7 +61,7 @@ struct Ctx {
     bool inited = false, ok = false;
     int  device = 0, sms = 0, smem_optin = 0;
     cudaStream_t s_comp = nullptr, s_comp2 = nullptr, s_h2d = nullptr, s_d2h = nullptr;
-    cudaEvent_t  ev_h2d[kMaxChunks], ev_k0[kMaxChunks], ev_k1[kMaxChunks];
+    cudaEvent_t  ev_h2d[kMaxChunks], ev_d2h[kMaxChunks], ev_k0[kMaxChunks], ev_k1[kMaxChunks];
     cudaEvent_t  ev_t0 = nullptr, ev_t1 = nullptr;
     DevBuf vels, depths, nl, off, dep, tobs, sigma, timeP, pout, logL, arena, voro, vsorted,
         idxar, arparb, sched, mh_ll, mh_out, mh_kp, mh_lpr;
@@ -73,6 +77,13 @@ struct Ctx {
     double        chain_armx  = 0.5;
     void  *pin = nullptr;          // pinned staging for small calls
     size_t pin_cap = 0;
+    // pinned ring for callers whose arrays are pageable (R vectors, Fortran arrays, numpy)
+    void  *stage = nullptr;
+    size_t stage_cap = 0;
+    void  *stage_out = nullptr;    // pinned bounce buffer for logL
+    size_t stage_out_cap = 0;
+    cudaEvent_t ev_slot[4] = {nullptr, nullptr, nullptr, nullptr};
+    int opt_stage = -1;            // -1 automatic (stage pageable inputs), 0 never, 1 always
     // options (<= 0: automatic)
     int opt_variant = -1, opt_threads = 0, opt_tile_models = 0, opt_tile_sources = 0,
         opt_chunk_models = 0, opt_ctas = 0, opt_logl_shuffle = 0, opt_comp_streams = 0, opt_static_tiles = 0;
@@ -141,6 +152,7 @@ int ensure_init(int device = -1) {
     CK(cudaStreamCreateWithFlags(&g.s_d2h, cudaStreamNonBlocking));
     for (int i = 0; i < kMaxChunks; ++i) {
         CK(cudaEventCreateWithFlags(&g.ev_h2d[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g.ev_d2h[i], cudaEventDisableTiming));
         CK(cudaEventCreate(&g.ev_k0[i]));
         CK(cudaEventCreate(&g.ev_k1[i]));
     }
@@ -313,6 +325,68 @@ int run_host_small(const HostCall &h, const TileCfg &cfg, int ldz) {
     return 0;
 }
 
+// Is this host pointer ordinary pageable memory (not pinned, not registered, not managed)?
+bool is_pageable(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// Copy into the pinned ring with non-temporal stores: the destination is only read by the DMA
+// engine, so it need not be fetched into (nor kept in) the caches; on a bandwidth-bound host this
+// is a third less memory traffic than memcpy's read-for-ownership.  dst is 16-byte aligned.
+void stream_copy(void *dst, const void *src, size_t bytes) {
+#if defined(__x86_64__)
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        char *d = static_cast<char *>(dst);
+        const char *s = static_cast<const char *>(src);
+        size_t i = 0;
+        for (; i + 64 <= bytes; i += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + i));
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + i + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + i + 32));
+            const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + i + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i *>(d + i), a);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(d + i + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(d + i + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(d + i + 48), e);
+        }
+        _mm_sfence();
+        if (i < bytes) memcpy(d + i, s + i, bytes - i);
+        return;
+    }
+#endif
+    memcpy(dst, src, bytes);
+}
+
+// the copy split over a few host threads: one core moves a few GB/s, the H2D link takes 50+
+void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+    constexpr size_t kMinPerThread = 1u << 20;
+    static const unsigned cap = [] {
+        const char *e = getenv("RTB200_COPY_THREADS");
+        const unsigned hw = std::thread::hardware_concurrency();
+        return e && atoi(e) > 0 ? (unsigned)atoi(e) : std::max(1u, std::min(hw / 2, 8u));
+    }();
+    size_t nt = std::min<size_t>(cap, std::max<size_t>(1, bytes / kMinPerThread));
+    if (nt <= 1) {
+        stream_copy(dst, src, bytes);
+        return;
+    }
+    const size_t part = (bytes / nt + 63) & ~(size_t)63;
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nt; ++t) {
+        const size_t o = t * part;
+        if (o >= bytes) break;
+        th.emplace_back([=] { stream_copy((char *)dst + o, (const char *)src + o, std::min(part, bytes - o)); });
+    }
+    stream_copy(dst, src, std::min(part, bytes));
+    for (auto &t : th) t.join();
+}
+
 // Host buffers in, host buffers out: chunked over the model axis so the copy of chunk j+1
 // and the read-back of chunk j-1 overlap the kernel of chunk j.
 int run_host(const HostCall &h) {
@@ -373,25 +447,73 @@ int run_host(const HostCall &h) {
     const int nchunks = (int)(1 + (B > lead ? (B - lead + chunk - 1) / chunk : 0));
 
     const double logc = h.logL ? log_norm_const(h.nsrc) : 0.0;
+    // A cudaMemcpyAsync from pageable memory is staged by the driver on the calling thread and
+    // blocks it, so copy and compute no longer overlap.  Pageable inputs (what R vectors, Fortran
+    // arrays and numpy arrays are) go through a pinned ring instead: a few host threads copy chunk
+    // j+1 into its slot while the GPU works on chunk j, and the H2D from the slot is asynchronous.
+    const size_t row_bytes = (size_t)h.ldv * 8 + (size_t)ldz * 8 + 4 + (h.sigma ? 8 : 0) + (h.idxar ? 12 : 0);
+    const bool stage = g.opt_stage == 1 || (g.opt_stage < 0 && is_pageable(h.vels) && B * row_bytes > (8u << 20));
+    constexpr int kSlots = 4;
+    const size_t slot_models = std::max(chunk, lead);
+    auto up64 = [](size_t x) { return (x + 63) & ~(size_t)63; };
+    const size_t so_v = 0, so_z = so_v + up64(slot_models * h.ldv * 8), so_n = so_z + up64(slot_models * ldz * 8),
+                 so_s = so_n + up64(slot_models * 4), so_i = so_s + up64(slot_models * 8),
+                 so_a = so_i + up64(slot_models * 4), slot_bytes = so_a + up64(slot_models * 8);
+    if (stage) {
+        if (g.stage_cap < kSlots * slot_bytes) {
+            if (g.stage) cudaFreeHost(g.stage);
+            g.stage = nullptr; g.stage_cap = 0;
+            CK(cudaMallocHost(&g.stage, kSlots * slot_bytes));
+            g.stage_cap = kSlots * slot_bytes;
+        }
+        for (int i = 0; i < kSlots; ++i)
+            if (!g.ev_slot[i]) CK(cudaEventCreateWithFlags(&g.ev_slot[i], cudaEventDisableTiming));
+    }
+    // logL comes back through a pinned bounce buffer when the caller's array is pageable
+    double *logL_host = h.logL;
+    if (h.logL && (g.opt_stage == 1 || (g.opt_stage < 0 && is_pageable(h.logL)))) {
+        if (g.stage_out_cap < B * 8) {
+            if (g.stage_out) cudaFreeHost(g.stage_out);
+            g.stage_out = nullptr; g.stage_out_cap = 0;
+            CK(cudaMallocHost(&g.stage_out, B * 8 + 4096));
+            g.stage_out_cap = B * 8 + 4096;
+        }
+        logL_host = static_cast<double *>(g.stage_out);
+    }
     for (int j = 0; j < nchunks; ++j) {
         const size_t j0 = j == 0 ? 0 : lead + (size_t)(j - 1) * chunk;
         const size_t j1 = std::min(B, j == 0 ? lead : j0 + chunk), nb = j1 - j0;
-        CK(cudaMemcpyAsync(g.vels.as<double>() + j0 * h.ldv, h.vels + j0 * h.ldv, nb * h.ldv * 8,
-                           cudaMemcpyHostToDevice, g.s_h2d));
-        if (ldz > 0)
-            CK(cudaMemcpyAsync(g.depths.as<double>() + j0 * ldz, h.depths + j0 * ldz,
-                               nb * ldz * 8, cudaMemcpyHostToDevice, g.s_h2d));
-        CK(cudaMemcpyAsync(g.nl.as<int>() + j0, h.nlayers + j0, nb * 4, cudaMemcpyHostToDevice,
-                           g.s_h2d));
-        if (h.sigma)
-            CK(cudaMemcpyAsync(g.sigma.as<double>() + j0, h.sigma + j0, nb * 8,
-                               cudaMemcpyHostToDevice, g.s_h2d));
-        if (h.idxar) {
-            CK(cudaMemcpyAsync(g.idxar.as<int>() + j0, h.idxar + j0, nb * 4, cudaMemcpyHostToDevice,
-                               g.s_h2d));
-            CK(cudaMemcpyAsync(g.arparb.as<double>() + j0, h.arpar + j0, nb * 8,
-                               cudaMemcpyHostToDevice, g.s_h2d));
+        const double *sv = h.vels + j0 * h.ldv, *sz = ldz > 0 ? h.depths + j0 * ldz : nullptr;
+        const int    *sn = h.nlayers + j0, *si = h.idxar ? h.idxar + j0 : nullptr;
+        const double *ss = h.sigma ? h.sigma + j0 : nullptr, *sa = h.idxar ? h.arpar + j0 : nullptr;
+        if (stage) {
+            const int slot = j % kSlots;
+            char *base = static_cast<char *>(g.stage) + (size_t)slot * slot_bytes;
+            if (j >= kSlots) CK(cudaEventSynchronize(g.ev_slot[slot]));     // the slot's last H2D is done
+            parallel_memcpy(base + so_v, sv, nb * h.ldv * 8);
+            if (sz) parallel_memcpy(base + so_z, sz, nb * ldz * 8);
+            memcpy(base + so_n, sn, nb * 4);
+            if (ss) memcpy(base + so_s, ss, nb * 8);
+            if (si) { memcpy(base + so_i, si, nb * 4); memcpy(base + so_a, sa, nb * 8); }
+            sv = reinterpret_cast<double *>(base + so_v);
+            sz = sz ? reinterpret_cast<double *>(base + so_z) : nullptr;
+            sn = reinterpret_cast<int *>(base + so_n);
+            ss = ss ? reinterpret_cast<double *>(base + so_s) : nullptr;
+            si = si ? reinterpret_cast<int *>(base + so_i) : nullptr;
+            sa = sa ? reinterpret_cast<double *>(base + so_a) : nullptr;
         }
+        CK(cudaMemcpyAsync(g.vels.as<double>() + j0 * h.ldv, sv, nb * h.ldv * 8,
+                           cudaMemcpyHostToDevice, g.s_h2d));
+        if (sz)
+            CK(cudaMemcpyAsync(g.depths.as<double>() + j0 * ldz, sz, nb * ldz * 8, cudaMemcpyHostToDevice,
+                               g.s_h2d));
+        CK(cudaMemcpyAsync(g.nl.as<int>() + j0, sn, nb * 4, cudaMemcpyHostToDevice, g.s_h2d));
+        if (ss) CK(cudaMemcpyAsync(g.sigma.as<double>() + j0, ss, nb * 8, cudaMemcpyHostToDevice, g.s_h2d));
+        if (si) {
+            CK(cudaMemcpyAsync(g.idxar.as<int>() + j0, si, nb * 4, cudaMemcpyHostToDevice, g.s_h2d));
+            CK(cudaMemcpyAsync(g.arparb.as<double>() + j0, sa, nb * 8, cudaMemcpyHostToDevice, g.s_h2d));
+        }
+        if (stage) CK(cudaEventRecord(g.ev_slot[j % kSlots], g.s_h2d));
         CK(cudaEventRecord(g.ev_h2d[j], g.s_h2d));
 
         BatchArgs a{};
@@ -430,10 +552,21 @@ int run_host(const HostCall &h) {
         if (h.p_out)
             CK(cudaMemcpyAsync(h.p_out + j0 * S, a.p_out, nb * S * 8, cudaMemcpyDeviceToHost,
                                g.s_d2h));
-        if (h.logL)
-            CK(cudaMemcpyAsync(h.logL + j0, a.logL, nb * 8, cudaMemcpyDeviceToHost, g.s_d2h));
+        if (h.logL) {
+            CK(cudaMemcpyAsync(logL_host + j0, a.logL, nb * 8, cudaMemcpyDeviceToHost, g.s_d2h));
+            if (logL_host != h.logL) CK(cudaEventRecord(g.ev_d2h[j], g.s_d2h));
+        }
     }
     CK(cudaEventRecord(g.ev_t1, g.s_d2h));
+    if (h.logL && logL_host != h.logL) {
+        // hand the chunks' logL to the caller's array as they arrive, under the later chunks' work
+        for (int j = 0; j < nchunks; ++j) {
+            const size_t j0 = j == 0 ? 0 : lead + (size_t)(j - 1) * chunk;
+            const size_t j1 = std::min(B, j == 0 ? lead : j0 + chunk);
+            CK(cudaEventSynchronize(g.ev_d2h[j]));
+            memcpy(h.logL + j0, logL_host + j0, (j1 - j0) * 8);
+        }
+    }
     CK(cudaStreamSynchronize(g.s_d2h));
     CK(cudaStreamSynchronize(g.s_comp));
     CK(cudaStreamSynchronize(g.s_comp2));
@@ -760,6 +893,17 @@ int rtb200_mh_step_device(const int *d_k, double *d_voro, double *d_logL, int B,
                           const double *prior, const double *d_src_offset,
                           const double *d_src_depth, const double *d_tobs, int NSrc,
                           int *d_accept, void *stream) {
+    return rtb200_mh_step_device_ev(d_k, d_voro, d_logL, B, ldk, d_ivo, d_iwhich, d_cauchy, d_uacc,
+                                    d_beta, d_sigma, prior, d_src_offset, d_src_depth, d_tobs, NSrc,
+                                    d_accept, stream, nullptr);
+}
+
+int rtb200_mh_step_device_ev(const int *d_k, double *d_voro, double *d_logL, int B, int ldk,
+                             const int *d_ivo, const int *d_iwhich, const double *d_cauchy,
+                             const double *d_uacc, const double *d_beta, const double *d_sigma,
+                             const double *prior, const double *d_src_offset,
+                             const double *d_src_depth, const double *d_tobs, int NSrc,
+                             int *d_accept, void *stream, void *beta_ready_event) {
     if (int rc = ensure_init()) return rc;
     g.err.clear();
     if (B <= 0) return 0;
@@ -779,6 +923,8 @@ int rtb200_mh_step_device(const int *d_k, double *d_voro, double *d_logL, int B,
     CK(cudaEventRecord(g.ev_k0[0], st));
     CK(rtb::launch_batch(a, cfg, st));
     CK(cudaEventRecord(g.ev_k1[0], st));
+    // the proposal and its likelihood do not read beta; only the accept test does
+    if (beta_ready_event) CK(cudaStreamWaitEvent(st, (cudaEvent_t)beta_ready_event, 0));
     CK(rtb::launch_mh_accept(d_k, d_voro, g.vsorted.as<double>(), d_logL, g.mh_ll.as<double>(),
                              g.mh_out.as<int>(), d_uacc, d_beta, B, ldk, d_accept, st));
     g.launches += 3;
@@ -999,6 +1145,35 @@ int rtb200_ar_step_device(const int *d_k, const double *d_voro, double *d_logL,
     return 0;
 }
 
+int rtb200_swap_pack_device(const double *d_logL, const double *d_beta, int n, double *d_out,
+                            void *stream) {
+    if (int rc = ensure_init()) return rc;
+    g.err.clear();
+    if (n <= 0) return 0;
+    if (!d_logL || !d_beta || !d_out) return fail("rtb200_swap_pack_device needs logL, beta and out");
+    cudaStream_t st = stream ? (cudaStream_t)stream : g.s_comp;
+    CK(rtb::launch_swap_pack(d_logL, d_beta, n, d_out, st));
+    g.launches++;
+    if (!stream) CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int rtb200_swap_round_device(const double *d_all, int n, int lo, int n_local,
+                             unsigned long long seed, unsigned long long round,
+                             double *d_beta_local, int *d_accept, int *d_partner, void *stream) {
+    if (int rc = ensure_init()) return rc;
+    g.err.clear();
+    if (n <= 0 || n_local <= 0) return 0;
+    if (!d_all || !d_beta_local) return fail("rtb200_swap_round_device needs the gathered pairs and beta_local");
+    if (lo < 0 || lo + n_local > n) return fail("rtb200_swap_round_device: [lo, lo + n_local) must lie inside [0, n)");
+    if (n > (1 << 30)) return fail("rtb200_swap_round_device: at most 2^30 chains");
+    cudaStream_t st = stream ? (cudaStream_t)stream : g.s_comp;
+    CK(rtb::launch_swap_round(d_all, n, lo, n_local, seed, round, d_beta_local, d_accept, d_partner, st));
+    g.launches++;
+    if (!stream) CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int rtb200_init(int device) { return ensure_init(device); }
 
 void rtb200_shutdown(void) {
@@ -1008,12 +1183,18 @@ void rtb200_shutdown(void) {
     if (g.pin) cudaFreeHost(g.pin);
     g.pin = nullptr;
     g.pin_cap = 0;
+    if (g.stage) cudaFreeHost(g.stage);
+    if (g.stage_out) cudaFreeHost(g.stage_out);
+    g.stage = g.stage_out = nullptr;
+    g.stage_cap = g.stage_out_cap = 0;
+    for (auto &e : g.ev_slot) { if (e) cudaEventDestroy(e); e = nullptr; }
     for (DevBuf *b : {&g.vels, &g.depths, &g.nl, &g.off, &g.dep, &g.tobs, &g.sigma,
                       &g.timeP, &g.pout, &g.logL, &g.arena, &g.voro, &g.vsorted, &g.idxar, &g.arparb,
                       &g.sched, &g.mh_ll, &g.mh_out, &g.mh_kp, &g.mh_lpr})
         b->release();
     for (int i = 0; i < kMaxChunks; ++i) {
         cudaEventDestroy(g.ev_h2d[i]);
+        cudaEventDestroy(g.ev_d2h[i]);
         cudaEventDestroy(g.ev_k0[i]);
         cudaEventDestroy(g.ev_k1[i]);
     }
@@ -1052,6 +1233,7 @@ int rtb200_set_option(const char *name, double value) {
     else if (!strcmp(name, "comp_streams")) g.opt_comp_streams = v;
     else if (!strcmp(name, "static_tiles")) g.opt_static_tiles = v > 0 ? 1 : 0;
     else if (!strcmp(name, "logl_shuffle")) g.opt_logl_shuffle = v > 0 ? 1 : 0;
+    else if (!strcmp(name, "stage_pageable")) g.opt_stage = v < 0 ? -1 : (v > 0 ? 1 : 0);
     else return -1;
     return 0;
 }

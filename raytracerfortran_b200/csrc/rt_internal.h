@@ -118,6 +118,11 @@ cudaError_t launch_ar_accept(int *idxar, double *arpar, const int *idx_prop, con
                              const double *logarp, double *logL, const double *logL_prop,
                              const int *outside, const double *u_acc, const double *beta, int B,
                              int *accept, cudaStream_t st);
+cudaError_t launch_swap_pack(const double *logL, const double *beta, int n, double *out,
+                             cudaStream_t st);
+cudaError_t launch_swap_round(const double *all, int n, int lo, int n_local, unsigned long long seed,
+                              unsigned long long round, double *beta_local, int *accept,
+                              int *partner, cudaStream_t st);
 int         max_ctas_per_sm(const TileCfg &c);   // occupancy of the batch kernel for this geometry
 cudaError_t fp64_peak(double *tflops, int repeats, cudaStream_t st);
 cudaError_t fastpath_selftest(double samples, unsigned long long seed, double *mismatches,

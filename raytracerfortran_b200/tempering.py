@@ -81,6 +81,9 @@ def tempering_swap_round(logL_local, beta_local, seed, round_index, group=None):
     n_local = logL_local.numel()
     rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
     logL_all, beta_all = allgather_replicas(logL_local, beta_local, group)
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if logL_all.size != world * n_local:
+        raise ValueError("tempering_swap_round needs the same number of replicas on every rank")
     pairs, accept = swap_decisions(logL_all, beta_all, seed, round_index)
     new_all = apply_swaps(beta_all, pairs, accept)
     mine = new_all[rank * n_local:(rank + 1) * n_local]
@@ -129,36 +132,110 @@ def mh_accept(logL_cur, logL_new, beta, u, logPr_new=None, outside=None):
     return accept
 
 
+class SwapRound:
+    """The swap round of parallel tempering with the decisions taken on the device
+    (rtb200_swap_pack_device -> all-gather of 16 bytes per chain -> rtb200_swap_round_device;
+    TEMPSWP_MH, prjmh_temper_rf.f90:1329-1384).
+
+    One object per set of local chains: it owns the packed / gathered buffers and a side stream.
+    `launch` enqueues the round on the side stream behind whatever the caller's stream has done so
+    far and returns at once; `wait` makes the caller's stream wait for the new betas.  Between the
+    two the caller can enqueue work that does not read beta -- the next step's proposal and
+    likelihood kernels -- so the collective and the swap kernel run under it
+    ("overlap it with the next step's proposal generation").  Every rank derives the
+    same pairing and decisions from (seed, round_index); CUDA tensors only (no CPU path)."""
+
+    def __init__(self, n_local, device, group=None, want_info=False):
+        self.group = group
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.distributed else 1
+        self.rank = dist.get_rank(group) if self.distributed else 0
+        self.n_local, self.n = int(n_local), int(n_local) * self.world
+        if self.distributed:                       # every rank must hold the same number of chains
+            cnt = torch.tensor([self.n_local], dtype=torch.int64, device=device)
+            lo, hi = cnt.clone(), cnt.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+            if int(lo) != int(hi):
+                raise ValueError("SwapRound needs the same number of chains on every rank")
+        f64 = torch.float64
+        self.mine = torch.empty((self.n_local, 2), dtype=f64, device=device)
+        self.all = torch.empty((self.n, 2), dtype=f64, device=device) if self.distributed else self.mine
+        self.accept = torch.empty((max(self.n // 2, 1),), dtype=torch.int32, device=device) if want_info else None
+        self.partner = torch.empty((self.n_local,), dtype=torch.int32, device=device) if want_info else None
+        self.side = torch.cuda.Stream(device=device)
+        self.ready = torch.cuda.Event()
+        self.done = torch.cuda.Event()
+        self.device = device
+
+    def launch(self, logL_local, beta_local, seed, round_index, beta_out=None, stream=None):
+        """Enqueue one round.  beta_out (default: beta_local, in place) receives the new betas."""
+        from . import _lib
+        from .device import _ensure_device, _ptr
+        dev = self.device
+        _ensure_device(dev.index if dev.index is not None else torch.cuda.current_device())
+        f64 = torch.float64
+        if beta_out is None:
+            beta_out = beta_local
+        cur = stream if stream is not None else torch.cuda.current_stream(dev)
+        self.ready.record(cur)
+        lib = _lib.load()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ready)
+            h = self.side.cuda_stream
+            _lib.check(lib.rtb200_swap_pack_device(_ptr(logL_local, f64), _ptr(beta_local, f64),
+                                                   self.n_local, _ptr(self.mine, f64), h))
+            if self.distributed:
+                dist.all_gather_into_tensor(self.all, self.mine, group=self.group)
+            _lib.check(lib.rtb200_swap_round_device(
+                _ptr(self.all, f64), self.n, self.rank * self.n_local, self.n_local,
+                int(seed) & 0xFFFFFFFFFFFFFFFF, int(round_index) & 0xFFFFFFFFFFFFFFFF,
+                _ptr(beta_out, f64), _ptr(self.accept, torch.int32), _ptr(self.partner, torch.int32), h))
+            self.done.record(self.side)
+        return self.done
+
+    def wait(self, stream=None):
+        (stream if stream is not None else torch.cuda.current_stream(self.device)).wait_event(self.done)
+
+
+_swap_rounds = {}
+
+
 def tempering_swap_round_device(logL_local, beta_local, seed, round_index, group=None):
-    """The swap round without leaving the device: all-gather, pairing, TEMPSWP_MH's accept rule
-    (prjmh_temper_rf.f90:1341-1344) and the beta exchange are tensor operations on the device the
-    replicas live on, so an MCMC step never synchronises with the host.  Every rank seeds an
-    identical device generator from (seed, round_index) and therefore derives the same pairs and
-    the same decisions.  Returns (new beta_local, info) where info holds device tensors
-    `pairs_i`, `pairs_j`, `accept`."""
-    dev = logL_local.device
-    n_local = logL_local.numel()
-    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-    rank = dist.get_rank(group) if distributed else 0
-    mine = torch.stack([logL_local.to(torch.float64), beta_local.to(torch.float64)], dim=1).contiguous()
-    if distributed:
-        allr = torch.empty((dist.get_world_size(group) * n_local, 2), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(allr, mine, group=group)
-    else:
-        allr = mine
-    logL, beta = allr[:, 0], allr[:, 1]
-    n = logL.numel()
-    g = torch.Generator(device=dev)
-    g.manual_seed((int(seed) * 1_000_003 + int(round_index)) & 0x7FFFFFFFFFFFFFFF)
-    perm = torch.randperm(n, generator=g, device=dev)
-    npair = n // 2
-    i, j = perm[:npair], perm[npair:2 * npair]
-    u = torch.rand(npair, generator=g, device=dev, dtype=torch.float64)
-    accept = u <= torch.exp((beta[j] - beta[i]) * (logL[i] - logL[j]))
-    new = beta.clone()
-    new[i] = torch.where(accept, beta[j], beta[i])
-    new[j] = torch.where(accept, beta[i], beta[j])
-    return new[rank * n_local:(rank + 1) * n_local].clone(), {"pairs_i": i, "pairs_j": j, "accept": accept}
+    """One swap round without leaving the device, in stream order (launch + wait of a cached
+    SwapRound).  Returns (new beta_local, info) with info = {"accept": [n/2] i32 per pair,
+    "partner": [n_local] i32 (see rtb200_swap_round_device)} as device tensors."""
+    if not logL_local.is_cuda:
+        raise ValueError("tempering_swap_round_device needs CUDA tensors (there is no CPU path); "
+                         "tempering_swap_round takes the decisions on the host")
+    key = (logL_local.device, logL_local.numel(), id(group))
+    sr = _swap_rounds.get(key)
+    if sr is None:
+        sr = _swap_rounds[key] = SwapRound(logL_local.numel(), logL_local.device, group, want_info=True)
+    out = torch.empty_like(beta_local)
+    sr.launch(logL_local, beta_local, seed, round_index, beta_out=out)
+    sr.wait()
+    return out, {"accept": sr.accept, "partner": sr.partner}
+
+
+def assign_ladder(beta_current, ladder):
+    """Hand a new ladder (LadderAdapter.update: ordered T = 1 first) to chains whose betas have
+    been exchanged by swap rounds: the chain holding the r-th largest beta gets the r-th largest
+    new one, so every state keeps its place in the temperature order -- the reference reassigns
+    beta_pt by chain slot and its swaps move states, not temperatures
+    (prjmh_temper_rf.f90:373-383, :1351-1357).  Works on numpy arrays or torch tensors."""
+    if isinstance(beta_current, torch.Tensor):
+        lad = torch.as_tensor(np.sort(np.asarray(ladder, dtype=np.float64))[::-1].copy(),
+                              device=beta_current.device)
+        order = torch.argsort(beta_current, descending=True, stable=True)
+        out = torch.empty_like(beta_current)
+        out[order] = lad
+        return out
+    cur = np.asarray(beta_current, dtype=np.float64)
+    order = np.argsort(-cur, kind="stable")
+    out = np.empty_like(cur)
+    out[order] = np.sort(np.asarray(ladder, dtype=np.float64))[::-1]
+    return out
 
 
 class LadderAdapter:
@@ -169,7 +246,8 @@ class LadderAdapter:
     shrinks by 2 % if it is above 0.5, and the betas are reassigned as 1/dTlog**(it-1).
 
     `update(accept)` takes the accept mask of one swap round (any array-like of booleans) and
-    returns the new ladder (numpy array, T = 1 chains first) when it changed, else None."""
+    returns the new ladder (numpy array, T = 1 chains first: ordered by ladder index, NOT by
+    replica -- hand it to the replicas with `assign_ladder`) when it changed, else None."""
 
     def __init__(self, n_replicas, dTlog, n_cold=1, acceptance_window=150):   # rjmcmc_com.f90:159
         self.n, self.dTlog, self.n_cold = int(n_replicas), float(dTlog), int(n_cold)

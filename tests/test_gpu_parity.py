@@ -42,6 +42,7 @@ def _reset_options():
     for name in ("variant", "threads", "tile_models", "tile_sources", "chunk_models", "ctas_per_sm",
                  "comp_streams", "static_tiles"):
         rt.set_option(name, -1 if name == "variant" else 0)
+    rt.set_option("stage_pageable", -1)
 
 
 @pytest.fixture(autouse=True)
@@ -344,3 +345,24 @@ def test_warp_shuffle_likelihood_reduction_option():
         rt.set_option("logl_shuffle", 0)
     assert_bitexact(got["timeP"], ref["timeP"], "timeP")
     assert_logl_close(got["logL"], ref["logL"], nsrc, sigma)
+
+
+def test_pageable_inputs_through_the_pinned_ring():
+    """Host arrays that are ordinary pageable memory are staged through the pinned ring (forced
+    here for a batch small enough to compare with the oracle, with more chunks than ring slots);
+    same bits as the direct path, logL through the bounce buffer, AR arrays included."""
+    B, nsrc = 6000, 24
+    v, z, nl = workloads.make_models(B, 10, 17)
+    so, sd = workloads.make_sources(nsrc, 17)
+    tobs, sigma = workloads.make_observations(np.ones(nsrc), B, 17)
+    ref = oracle.dff_batch(v, z, nl, so, sd, tobs=tobs, sigma=sigma, want_p=True)
+    rt.set_option("stage_pageable", 0)
+    direct = rt.dff_batch(v, z, nl, so, sd, tobs=tobs, sigma=sigma, want_p=True)
+    for opts in ({"stage_pageable": 1}, {"stage_pageable": 1, "chunk_models": 500},
+                 {"stage_pageable": 1, "chunk_models": 777, "comp_streams": 1}):
+        for k_, v_ in opts.items():
+            rt.set_option(k_, v_)
+        got = rt.dff_batch(v, z, nl, so, sd, tobs=tobs, sigma=sigma, want_p=True)
+        assert_bitexact(got["timeP"], ref["timeP"], f"timeP {opts}")
+        assert_bitexact(got["p"], ref["p"], f"p {opts}")
+        assert np.array_equal(got["logL"].view(np.uint64), direct["logL"].view(np.uint64))

@@ -68,14 +68,16 @@ def _worker(rank, world, port, ret):
         for rnd in range(5):
             beta, st = tempering.tempering_swap_round(logL, beta, seed, rnd)
             history.append((beta.numpy().copy(), st["accept"].copy(), st["pairs"].copy()))
-        # the all-device variant: same rule, device-side pairing; ranks must agree
+        # the device-side scheme (rtb200_swap_round_device), restated by oracle/tempering_ref.py:
+        # every rank applies it to what it gathered; ranks must agree on pairs, decisions, betas
+        from oracle import tempering_ref
         beta_d = torch.from_numpy(beta_all[lo:hi].copy())
         dev_hist = []
         for rnd in range(5):
-            before = beta_d.clone()
-            beta_d, info = tempering.tempering_swap_round_device(logL, beta_d, seed, rnd)
-            dev_hist.append((before.numpy().copy(), beta_d.numpy().copy(), info["pairs_i"].numpy().copy(),
-                             info["pairs_j"].numpy().copy(), info["accept"].numpy().copy()))
+            g_l, g_b = tempering.allgather_replicas(logL, beta_d)
+            new, pairs, acc, _ = tempering_ref.swap_round(g_l, g_b, seed, rnd)
+            dev_hist.append((g_b.copy(), new.copy(), pairs[:, 0].copy(), pairs[:, 1].copy(), acc.copy()))
+            beta_d = torch.from_numpy(new[lo:hi].copy())
         ret[rank] = history
         ret[("dev", rank)] = dev_hist
     finally:
@@ -104,10 +106,10 @@ def test_swap_round_world_size_2_gloo():
     d0, d1 = ret[("dev", 0)], ret[("dev", 1)]
     ladder = tempering.temperature_ladder(8, 1.4)
     for rnd in range(5):
-        b0, n0, i0, j0, a0 = d0[rnd]
+        before, after, i0, j0, a0 = d0[rnd]
         b1, n1, i1, j1, a1 = d1[rnd]
         assert np.array_equal(i0, i1) and np.array_equal(j0, j1) and np.array_equal(a0, a1)
-        before, after = np.concatenate([b0, b1]), np.concatenate([n0, n1])
+        assert np.array_equal(before, b1) and np.array_equal(after, n1)
         assert sorted(after.tolist()) == sorted(ladder.tolist())
         for i, j, a in zip(i0, j0, a0):
             if a:
@@ -150,3 +152,49 @@ def test_ladder_adapter_follows_the_burn_in_rule():
     assert ad.update(acc) is None and ad.dTlog == d and abs(ad.acceptance_rate - 4 / 11) < 1e-15
     assert ad.update(np.zeros(11, bool), burn_in=False) is None and ad.dTlog == d    # after burn-in: only the rate
     assert ad.acceptance_rate == 0.0
+
+
+def test_philox4x32_10_known_answers():
+    """Random123's known-answer vectors for philox4x32-10 pin the generator both the oracle and the
+    swap kernel implement."""
+    from oracle import tempering_ref as t
+    h = lambda x: [int(np.asarray(v).reshape(-1)[0]) for v in x]
+    assert h(t.philox4x32_10((0, 0, 0, 0), (0, 0))) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert h(t.philox4x32_10((0xffffffff,) * 4, (0xffffffff, 0xffffffff))) == \
+        [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert h(t.philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0))) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_device_swap_scheme_reference():
+    """The counter-derived pairing is a perfect matching for any n, changes with the round, and the
+    decisions follow TEMPSWP_MH's rule (prjmh_temper_rf.f90:1339-1344)."""
+    from oracle import tempering_ref as t
+    rng = np.random.default_rng(8)
+    for n in (2, 3, 5, 64, 1000, 4097):
+        p = t.swap_perm(n, 11, 3)
+        assert sorted(p.tolist()) == list(range(n))
+        assert np.array_equal(p[:7], t.swap_perm(n, 11, 3, idx=np.arange(min(7, n))))
+        logL = rng.normal(-50, 30, n)
+        beta = tempering.temperature_ladder(n, 1.02)
+        new, pairs, acc, u = t.swap_round(logL, beta, 11, 3)
+        assert pairs.shape == (n // 2, 2) and len(set(pairs.ravel().tolist())) == 2 * (n // 2)
+        assert sorted(new.tolist()) == sorted(beta.tolist())
+        assert ((u >= 0) & (u < 1)).all()
+        for (i, j), a, uu in zip(pairs[:50], acc[:50], u[:50]):
+            lr = (beta[j] - beta[i]) * (logL[i] - logL[j])
+            assert bool(a) == (uu <= (math.exp(lr) if lr < 700 else math.inf))
+            assert (new[i], new[j]) == ((beta[j], beta[i]) if a else (beta[i], beta[j]))
+    assert not np.array_equal(t.swap_perm(64, 11, 3), t.swap_perm(64, 11, 4))
+    assert not np.array_equal(t.swap_perm(64, 11, 3), t.swap_perm(64, 12, 3))
+
+
+def test_assign_ladder_keeps_the_temperature_order():
+    """A new ladder goes to the chains by the rank of the beta they currently hold
+    (prjmh_temper_rf.f90:373-383 reassigns by slot; here swaps moved the betas, not the states)."""
+    cur = np.array([0.5, 1.0, 0.25, 0.7])
+    lad = tempering.temperature_ladder(4, 1.5)                     # 1, 1/1.5, 1/2.25, 1/3.375
+    out = tempering.assign_ladder(cur, lad)
+    assert np.array_equal(out, np.array([lad[2], lad[0], lad[3], lad[1]]))
+    out_t = tempering.assign_ladder(torch.from_numpy(cur), lad)
+    assert np.array_equal(out_t.numpy(), out)
