@@ -276,7 +276,9 @@ int         rtb200_device_count(void);        /* 0 without a driver / device    
  *          "logl_shuffle" (1: reduce the residuals of a model with a warp-shuffle tree instead of
  *          the reference's source order -- same terms, ~N ulp from the ordered sum; default 0);
  *          "stage_pageable" (-1 default: large pageable host inputs are copied by a few host
- *          threads into a pinned ring so that H2D stays asynchronous; 0 never; 1 always) */
+ *          threads into a pinned ring so that H2D stays asynchronous; 0 never; 1 always);
+ *          "latency_path" (1 default: a one-model call without likelihood -- dff_, TraceRays --
+ *          runs the one-warp-per-ray kernel on mapped pinned memory; 0: the batch kernel) */
 int         rtb200_set_option(const char *name, double value);
 /* stats of the last batched call: "kernel_ms", "total_ms", "launches" (cumulative),
  *          "tile_models", "tile_sources", "smem_bytes", "grid", "threads", "ctas_per_sm" */

@@ -70,6 +70,8 @@ def lib():
         _lib.orc_loglhood_voro.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, dp, C.c_double, dp, dp, dp]
         _lib.orc_loglhood_from_times_ar.restype = C.c_double
         _lib.orc_loglhood_from_times_ar.argtypes = [dp, dp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]
+        _lib.orc_set_enos.restype = None
+        _lib.orc_set_enos.argtypes = [C.c_int]
         _lib.orc_mh_step_batch.restype = None
         _lib.orc_mh_step_batch.argtypes = [ip, dp, dp, C.c_int, C.c_int, ip, ip, dp, dp, dp, dp, dp,
                                            dp, dp, C.c_int, dp, ip, dp, dp]
@@ -291,3 +293,8 @@ def batch_stats(vels, depths, nlayers, src_offset, src_depth):
     lib().orc_batch_stats(_p(v), _p(z), nl.ctypes.data_as(C.POINTER(C.c_int)), v.shape[0],
                           v.shape[1], z.shape[1], _p(so), _p(sd), so.size, C.byref(st))
     return st.as_dict()
+
+
+def set_enos(enos):
+    """ENOS switch of the move oracles (orc_set_enos): 1 = even-numbered order statistics prior."""
+    lib().orc_set_enos(1 if enos else 0)

@@ -541,6 +541,14 @@ static double chain_loglhood(int chain, int k, const double *vp, const double *z
  * prop_depth/prop_vp [k] (may be NULL) receive the proposal after INTERPLAYER_novar, *logL_prop
  * (may be NULL) its logL (untouched when outside).  Returns 1 accepted, 0 rejected, -1 rejected
  * because the proposal left the prior bounds (ioutside).                                     */
+/* ENOS (even-numbered order statistics prior, Green 1995; rjmcmc_com.f90) for the move oracles:
+ * 0 = Cauchy depth steps and no order-statistics terms, 1 = uniform depth step between the
+ * neighbouring nodes (PROPOSAL :1418-1431) and the prior ratios of DEATH_FULL :981-991 /
+ * BIRTH_FULL :1090-1098.  With ENOS = 1 the `cauchy` argument of a depth move carries the
+ * uniform deviate itself. */
+static int g_enos = 0;
+void orc_set_enos(int enos) { g_enos = enos ? 1 : 0; }
+
 int orc_mh_step_chain(int chain, int k, double *node_depth, double *node_vp, double *logL,
                 int ivo, int iwhich, double cauchy, double u_acc, double beta, double sigma,
                 const double *prior,
@@ -556,6 +564,14 @@ int orc_mh_step_chain(int chain, int k, double *node_depth, double *node_vp, dou
     memcpy(d, node_depth, sizeof(double) * (size_t)k);
     memcpy(v, node_vp, sizeof(double) * (size_t)k);
     double *tgt = (iwhich == 1) ? d : v;
+    double logPr = 0.0;
+    if (iwhich == 1 && g_enos) {                                 /* :1418-1431 */
+        const double zj = d[ivo - 1], zjm1 = d[ivo - 2];
+        const double zjp1 = (ivo == k) ? maxlim[0] : d[ivo];     /* hmx = maxlim(1) */
+        const double zp = zjm1 + cauchy * (zjp1 - zjm1);
+        d[ivo - 1] = zp;
+        logPr = log(zjp1 - zp) + log(zp - zjm1) - log(zjp1 - zj) - log(zj - zjm1);
+    } else
     tgt[ivo - 1] = tgt[ivo - 1] + scale[iwhich - 1] * cauchy;    /* :1405 / :1416 */
     if (iwhich == 1) d[ivo - 1] = fabs(d[ivo - 1]);              /* :1441-1443 */
     int ordered = 1;
@@ -582,7 +598,7 @@ int orc_mh_step_chain(int chain, int k, double *node_depth, double *node_vp, dou
     } else {
         const double ll = chain_loglhood(chain, k, v, d + 1, src_offset, src_depth, nsrc, tobs, sigma);
         if (logL_prop) *logL_prop = ll;
-        const double logPLratio = 0.0 + (ll - *logL) * beta;     /* :744-745, logPr = 0 (ENOS = 0) */
+        const double logPLratio = logPr + (ll - *logL) * beta;   /* :743-745 */
         if (u_acc >= exp(logPLratio)) {
             ret = 0;                                             /* :747-749 */
         } else {
@@ -630,13 +646,37 @@ int orc_bd_step_chain(int chain, int *k_io, double *node_depth, double *node_vp,
     memcpy(d, node_depth, sizeof(double) * (size_t)k);
     memcpy(v, node_vp, sizeof(double) * (size_t)k);
     int kn;
+    double et[6];                /* the order-statistics terms, added left to right as the Fortran does */
+    int net = 0, enos_bad = 0;
+    const double hmx = maxlim[0], kk = (double)k;
     if (i_bd == 1) {
         kn = k + 1;
-        d[k] = (maxlim[0] - minlim[0]) * u_z;                    /* :1035-1040 */
+        const double znew = (maxlim[0] - minlim[0]) * u_z;       /* :1035-1040 */
+        d[k] = znew;
         v[k] = minlim[1] + (maxlim[1] - minlim[1]) * u_v;        /* :1051 */
         orc_interplayer_novar(kn, d, v);                         /* :1057 */
+        if (g_enos) {                                            /* :1061-1073, :1090-1098 */
+            int iznew = 0;
+            for (int ivo = 1; ivo <= k; ++ivo)
+                if (d[ivo] - znew == 0.0) iznew = ivo + 1;       /* ziface(ivo) = voro(ivo+1,1) */
+            if (iznew == 0) enos_bad = 1;                        /* the reference would index voro(-1) */
+            else {
+                const double zj = d[iznew - 2];
+                const double zjp1 = (iznew > k) ? hmx : d[iznew];
+                et[0] = log(2.0 * kk + 2.0);  et[1] = log(2.0 * kk + 3.0);  et[2] = -(2.0 * log(hmx - hmin));
+                et[3] = log(znew - zj);       et[4] = log(zjp1 - znew);     et[5] = -log(zjp1 - zj);
+                net = 6;
+            }
+        }
     } else {
         kn = k - 1;
+        if (g_enos) {                                            /* :941-947, :981-991 */
+            const double zdel = d[idel - 1], zj = d[idel - 2];
+            const double zjp1 = (idel == k) ? hmx : d[idel];
+            et[0] = 2.0 * log(hmx - hmin);  et[1] = -log(2.0 * kk * (2.0 * kk + 1.0));
+            et[2] = log(zjp1 - zj);         et[3] = -log(zdel - zj);        et[4] = -log(zjp1 - zdel);
+            net = 5;
+        }
         d[idel - 1] = 0.0;                                       /* :948 */
         v[idel - 1] = 0.0;
         orc_interplayer_novar(k, d, v);                          /* :951-953 QSORTC2D over k nodes */
@@ -644,7 +684,12 @@ int orc_bd_step_chain(int chain, int *k_io, double *node_depth, double *node_vp,
         d[kn] = 0.0; v[kn] = 0.0;                                /* :959 */
         orc_interplayer_novar(kn, d, v);                         /* :962 */
     }
-    const double logPr = pk ? log(pk[kn - 1]) - log(pk[k - 1]) : 0.0;       /* :986 / :1094 */
+    double logPr = pk ? log(pk[kn - 1]) - log(pk[k - 1]) : 0.0;             /* :986 / :1094 */
+    if (g_enos && net) {                                                    /* :981-991 / :1090-1098 */
+        double acc = pk ? logPr + et[0] : et[0];
+        for (int i = 1; i < net; ++i) acc = acc + et[i];
+        logPr = acc;
+    }
     if (k_prop) *k_prop = kn;
     if (prop_depth) memcpy(prop_depth, d, sizeof(double) * (size_t)ldk);
     if (prop_vp) memcpy(prop_vp, v, sizeof(double) * (size_t)ldk);
@@ -659,6 +704,7 @@ int orc_bd_step_chain(int chain, int *k_io, double *node_depth, double *node_vp,
         if (ivo > 1 && (d[ivo - 1] < 0.0 || d[ivo - 1] > maxlim[0])) outside = 1;
         if ((v[ivo - 1] - minlim[1]) < 0.0 || (maxlim[1] - v[ivo - 1]) < 0.0) outside = 1;
     }
+    if (enos_bad) outside = 1;
     int ret;
     if (outside) {
         ret = -1;                                                /* :700-704 */

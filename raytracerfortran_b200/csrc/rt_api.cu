@@ -84,6 +84,10 @@ struct Ctx {
     size_t stage_out_cap = 0;
     cudaEvent_t ev_slot[4] = {nullptr, nullptr, nullptr, nullptr};
     int opt_stage = -1;            // -1 automatic (stage pageable inputs), 0 never, 1 always
+    // mapped pinned buffer of the one-model latency path (dff_ / TraceRays)
+    void  *lat = nullptr;
+    size_t lat_cap = 0;
+    int opt_latency = 1;           // 1: one-model calls take the latency kernel; 0: the batch kernel
     // options (<= 0: automatic)
     int opt_variant = -1, opt_threads = 0, opt_tile_models = 0, opt_tile_sources = 0,
         opt_chunk_models = 0, opt_ctas = 0, opt_logl_shuffle = 0, opt_comp_streams = 0, opt_static_tiles = 0;
@@ -387,6 +391,54 @@ void parallel_memcpy(void *dst, const void *src, size_t bytes) {
     for (auto &t : th) t.join();
 }
 
+// One model, no likelihood (dff_, dff7_, TraceRays): the call is pure latency.  Arguments are
+// copied into a mapped pinned buffer the kernel reads and writes directly (zero-copy over PCIe), so
+// the call is one memcpy, one launch of the one-warp-per-ray kernel, one stream synchronise.
+constexpr int kLatencyMaxSources = 8192;
+
+int run_host_latency(const HostCall &h) {
+    const int NL = std::max(h.nlayers[0], 0), S = h.nsrc;
+    const size_t n_in = (size_t)(2 * NL + 1) + 2 * (size_t)S, n_out = 2 * (size_t)S;
+    const size_t bytes = (n_in + n_out) * 8 + 192;
+    if (bytes > g.lat_cap) {
+        if (g.lat) cudaFreeHost(g.lat);
+        g.lat = nullptr; g.lat_cap = 0;
+        CK(cudaHostAlloc(&g.lat, 2 * bytes, cudaHostAllocMapped));
+        g.lat_cap = 2 * bytes;
+    }
+    double *in = static_cast<double *>(g.lat), *out = in + ((n_in + 7) & ~(size_t)7);
+    memcpy(in, h.vels, (size_t)(NL + 1) * 8);
+    if (NL > 0) memcpy(in + NL + 1, h.depths, (size_t)NL * 8);
+    memcpy(in + 2 * NL + 1, h.off, (size_t)S * 8);
+    memcpy(in + 2 * NL + 1 + S, h.dep, (size_t)S * 8);
+    double *d_in = nullptr;
+    CK(cudaHostGetDevicePointer((void **)&d_in, in, 0));
+    double *d_out = d_in + (out - in);
+    // completion flag after the outputs, on its own cache line
+    volatile int *flag = reinterpret_cast<volatile int *>(out + ((n_out + 7) & ~(size_t)7));
+    int *d_flag = reinterpret_cast<int *>(d_out + ((n_out + 7) & ~(size_t)7));
+    *flag = 0;
+    int single = 0;
+    CK(rtb::launch_dff_latency(in, d_in, NL, S, d_out, h.p_out ? 1 : 0, d_flag, &single, g.s_comp));
+    g.launches++;
+    if (single) {
+        // a single-CTA launch sets the flag after its last store: spinning on it is ~2 us
+        // quicker than the stream synchronise; give up after a while so a faulting kernel
+        // still surfaces as an error below
+        for (long spin = 0; *flag == 0 && spin < 4000000; ++spin) {}
+        if (*flag == 0) CK(cudaStreamSynchronize(g.s_comp));
+    } else {
+        CK(cudaStreamSynchronize(g.s_comp));
+    }
+    if (h.timeP) memcpy(h.timeP, out, (size_t)S * 8);
+    if (h.p_out) memcpy(h.p_out, out + S, (size_t)S * 8);
+    g.last = TileCfg{};
+    g.last.variant = 5;            // reported by rtb200_get_stat("variant")
+    g.last.threads = std::min(S, 32) * 32;
+    g.last.grid = (S + 31) / 32;
+    return 0;
+}
+
 // Host buffers in, host buffers out: chunked over the model axis so the copy of chunk j+1
 // and the read-back of chunk j-1 overlap the kernel of chunk j.
 int run_host(const HostCall &h) {
@@ -398,6 +450,11 @@ int run_host(const HostCall &h) {
     if (h.logL && (!h.tobs || !h.sigma)) return fail("logL needs tobs and sigma");
     const size_t B = (size_t)h.B, S = (size_t)h.nsrc;
     const int ldz = std::max(h.ldz, 0);
+    if (g.opt_latency && g.opt_variant < 0 && h.B == 1 && !h.logL && !h.kmode && !h.idxar &&
+        h.nsrc <= kLatencyMaxSources) {
+        const int nl0 = std::max(h.nlayers[0], 0);
+        if (nl0 + 1 <= h.ldv && nl0 <= ldz && nl0 <= 254) return run_host_latency(h);
+    }
 
     TileCfg cfg;
     if (int rc = choose_cfg(h.B, h.ldv, ldz, h.nsrc, true, cfg)) return rc;
@@ -461,7 +518,10 @@ int run_host(const HostCall &h) {
                  so_a = so_i + up64(slot_models * 4), slot_bytes = so_a + up64(slot_models * 8);
     if (stage) {
         if (g.stage_cap < kSlots * slot_bytes) {
-            if (g.stage) cudaFreeHost(g.stage);
+            if (g.lat) cudaFreeHost(g.lat);
+    g.lat = nullptr;
+    g.lat_cap = 0;
+    if (g.stage) cudaFreeHost(g.stage);
             g.stage = nullptr; g.stage_cap = 0;
             CK(cudaMallocHost(&g.stage, kSlots * slot_bytes));
             g.stage_cap = kSlots * slot_bytes;
@@ -1234,6 +1294,7 @@ int rtb200_set_option(const char *name, double value) {
     else if (!strcmp(name, "static_tiles")) g.opt_static_tiles = v > 0 ? 1 : 0;
     else if (!strcmp(name, "logl_shuffle")) g.opt_logl_shuffle = v > 0 ? 1 : 0;
     else if (!strcmp(name, "stage_pageable")) g.opt_stage = v < 0 ? -1 : (v > 0 ? 1 : 0);
+    else if (!strcmp(name, "latency_path")) g.opt_latency = v == 0 ? 0 : 1;
     else return -1;
     return 0;
 }

@@ -118,6 +118,8 @@ cudaError_t launch_ar_accept(int *idxar, double *arpar, const int *idx_prop, con
                              const double *logarp, double *logL, const double *logL_prop,
                              const int *outside, const double *u_acc, const double *beta, int B,
                              int *accept, cudaStream_t st);
+cudaError_t launch_dff_latency(const double *in_host, const double *in_dev, int NL, int S, double *out,
+                               int want_p, int *done_flag, int *single_cta, cudaStream_t st);
 cudaError_t launch_swap_pack(const double *logL, const double *beta, int n, double *out,
                              cudaStream_t st);
 cudaError_t launch_swap_round(const double *all, int n, int lo, int n_local, unsigned long long seed,

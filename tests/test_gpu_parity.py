@@ -43,6 +43,7 @@ def _reset_options():
                  "comp_streams", "static_tiles"):
         rt.set_option(name, -1 if name == "variant" else 0)
     rt.set_option("stage_pageable", -1)
+    rt.set_option("latency_path", 1)
 
 
 @pytest.fixture(autouse=True)
@@ -366,3 +367,53 @@ def test_pageable_inputs_through_the_pinned_ring():
         assert_bitexact(got["timeP"], ref["timeP"], f"timeP {opts}")
         assert_bitexact(got["p"], ref["p"], f"p {opts}")
         assert np.array_equal(got["logL"].view(np.uint64), direct["logL"].view(np.uint64))
+
+
+@pytest.mark.parametrize("NL,S", [(0, 1), (1, 7), (6, 20), (6, 33), (29, 500), (50, 64), (200, 40), (10, 8192)])
+def test_one_model_latency_kernel(NL, S):
+    """dff_ / TraceRays on one model run the one-warp-per-ray kernel on mapped pinned memory: the
+    oracle's bits in T and p, and the batch kernel's, for shallow and deep columns, one source and
+    thousands, near-critical rays and sources on interfaces."""
+    rng = np.random.default_rng(1000 * NL + S)
+    v = rng.uniform(1500, 10000, NL + 1)
+    z = np.sort(rng.uniform(100, 9500, NL))
+    so, sd = workloads.make_sources(S, NL + S, near_critical=(NL >= 29))
+    if NL >= 3:
+        sd[:3] = z[:3]                                   # sources exactly on interfaces
+    ref, p_ref, _ = oracle.trace_rays(v, z, so, sd)
+    got = rt.dff_batch(v[None, :], z[None, :] if NL else np.zeros((1, 0)), np.array([NL], np.int32), so, sd, want_p=True)
+    assert rt.get_stat("variant") == 5
+    assert_bitexact(got["timeP"][0], ref, "timeP latency kernel")
+    assert_bitexact(got["p"][0], p_ref, "p latency kernel")
+    t = rt.dff(v, z, so, sd)
+    assert_bitexact(t, ref, "dff_")
+    rt.set_option("latency_path", 0)
+    t2 = rt.dff(v, z, so, sd)
+    assert rt.get_stat("variant") != 5
+    assert_bitexact(t2, ref, "dff_ batch kernel")
+
+
+def test_one_model_latency_kernel_hostile_inputs():
+    rng = np.random.default_rng(4)
+    base_v = rng.uniform(1500, 10000, 8)
+    base_z = np.sort(rng.uniform(100, 9000, 7))
+    so, sd = workloads.make_sources(40, 3)
+    so[1], sd[2], so[3], sd[4], so[5] = 0.0, 0.0, -50.0, -10.0, np.inf
+    so[6], sd[7] = np.nan, np.nan
+    for case in range(8):
+        v, z = base_v.copy(), base_z.copy()
+        if case == 1: z[3] = z[2]
+        if case == 2: v[2] = -v[2]
+        if case == 3: v[1] = 0.0
+        if case == 4: v *= 1e12
+        if case == 5: z = z[::-1].copy()
+        if case == 6: v[3] = np.nan
+        if case == 7: z[4] = np.inf
+        with np.errstate(all="ignore"):
+            ref, p_ref, _ = oracle.trace_rays(v, z, so, sd)
+        got = rt.dff_batch(v[None, :], z[None, :], np.array([7], np.int32), so, sd, want_p=True)
+        assert rt.get_stat("variant") == 5
+        for g_, w_, nm in ((got["timeP"][0], ref, "T"), (got["p"][0], p_ref, "p")):
+            nan = np.isnan(w_)
+            assert np.array_equal(np.isnan(g_), nan), (case, nm)
+            assert np.array_equal(g_[~nan].view(np.uint64), w_[~nan].view(np.uint64)), (case, nm)
