@@ -165,13 +165,17 @@ int rtb200_mh_step_device(const int *d_k, double *d_voro, double *d_logL, int B,
                           int *d_accept, void *stream);
 /* The same move with the accept test ordered behind a CUDA event (cudaEvent_t, may be NULL): the
  * proposal and likelihood kernels do not read d_beta, so a tempering swap round that is still
- * rewriting the betas on another stream (rtb200_swap_round_device) overlaps with them. */
+ * rewriting the betas on another stream (rtb200_swap_round_device) overlaps with them.
+ * enos = 1 selects the even-numbered order statistics prior of the parameter file (ENOS, Green
+ * 1995): a depth move draws the node uniformly between its neighbours -- d_cauchy[b] is then the
+ * uniform ran_uni itself -- and LOG(zjp1-zp)+LOG(zp-zjm1)-LOG(zjp1-zj)-LOG(zj-zjm1) enters the
+ * accept test as logPr (PROPOSAL, prjmh_temper_rf.f90:1418-1431, :743-745). */
 int rtb200_mh_step_device_ev(const int *d_k, double *d_voro, double *d_logL, int B, int ldk,
                           const int *d_ivo, const int *d_iwhich, const double *d_cauchy,
                           const double *d_uacc, const double *d_beta, const double *d_sigma,
                           const double *prior, const double *d_src_offset,
                           const double *d_src_depth, const double *d_tobs, int NSrc,
-                          int *d_accept, void *stream, void *beta_ready_event);
+                          int *d_accept, void *stream, void *beta_ready_event, int enos);
 
 /* n_moves consecutive calls of rtb200_mh_step_device in one: move m uses row m of d_ivo, d_iwhich,
  * d_cauchy, d_uacc and writes row m of d_accept (all [n_moves][B]).  The run is captured once into
@@ -184,6 +188,13 @@ int rtb200_mh_moves_device(const int *d_k, double *d_voro, double *d_logL, int B
                            const double *d_sigma, const double *prior, const double *d_src_offset,
                            const double *d_src_depth, const double *d_tobs, int NSrc,
                            int *d_accept, void *stream);
+/* The same with the ENOS switch of rtb200_mh_step_device_ev. */
+int rtb200_mh_moves_device_ex(const int *d_k, double *d_voro, double *d_logL, int B, int ldk,
+                           int n_moves, const int *d_ivo, const int *d_iwhich,
+                           const double *d_cauchy, const double *d_uacc, const double *d_beta,
+                           const double *d_sigma, const double *prior, const double *d_src_offset,
+                           const double *d_src_depth, const double *d_tobs, int NSrc,
+                           int *d_accept, void *stream, int enos);
 
 /* The birth/death move at the top of EXPLORE_MH_NOVARPAR (prjmh_temper_rf.f90:658-710) for B
  * independent chains on the device: move choice from ran_unik (:666-680: 1/3 birth, 1/3 death,
@@ -203,6 +214,16 @@ int rtb200_bd_step_device(int *d_k, double *d_voro, double *d_logL, int B, int l
                           const double *d_sigma, const double *prior, const double *pk, int kmin,
                           int kmax, const double *d_src_offset, const double *d_src_depth,
                           const double *d_tobs, int NSrc, int *d_accept, void *stream);
+/* The same with enos = 1: the order-statistics terms of DEATH_FULL (prjmh_temper_rf.f90:981-991)
+ * and BIRTH_FULL (:1090-1098) are added to logPr (after LOG(pk(k'))-LOG(pk(k)) when pk is given);
+ * a birth whose new node cannot be found among the sorted interfaces (the reference would index
+ * voro(-1,1)) is rejected as outside. */
+int rtb200_bd_step_device_ex(int *d_k, double *d_voro, double *d_logL, int B, int ldk,
+                          const double *d_uk, const int *d_idel, const double *d_uz,
+                          const double *d_uv, const double *d_uacc, const double *d_beta,
+                          const double *d_sigma, const double *prior, const double *pk, int kmin,
+                          int kmax, const double *d_src_offset, const double *d_src_depth,
+                          const double *d_tobs, int NSrc, int *d_accept, void *stream, int enos);
 
 /* The data-error move of EXPLORE_MH (prjmh_temper_rf.f90:545-575) for B independent chains on the
  * device: chains whose gate uniform is >= 0.10 propose sdparRT + pertsdsdRT*gauss (PROPOSAL_SDRT,

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "libraytrace_b200
 # every symbol include/raytrace_b200.h declares
 EXPORTS = (
     "dff_", "dff7_", "tracerays_", "__raymod_MOD_tracerays", "raymod_mp_tracerays_", "raymod_tracerays_", "dff_batch", "loglhood_batch", "loglhood_batch_ar", "loglhood_batch_voro",
-    "rtb200_dff_batch_device", "rtb200_mh_step_device", "rtb200_mh_step_device_ev", "rtb200_mh_moves_device", "rtb200_bd_step_device", "rtb200_sd_step_device", "rtb200_ar_step_device", "rtb200_set_chain_ar",
+    "rtb200_dff_batch_device", "rtb200_mh_step_device", "rtb200_mh_step_device_ev", "rtb200_mh_moves_device", "rtb200_mh_moves_device_ex", "rtb200_bd_step_device_ex", "rtb200_bd_step_device", "rtb200_sd_step_device", "rtb200_ar_step_device", "rtb200_set_chain_ar",
     "rtb200_swap_pack_device", "rtb200_swap_round_device",
     "rtb200_swap_pack_device", "rtb200_swap_round_device",
     "rtb200_init", "rtb200_shutdown", "rtb200_last_error", "rtb200_device_count",
@@ -61,7 +61,12 @@ def load():
     lib.rtb200_mh_step_device.restype = i
     lib.rtb200_mh_step_device.argtypes = [vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, dp, vp, vp, vp, i, vp, vp]
     lib.rtb200_mh_step_device_ev.restype = i
-    lib.rtb200_mh_step_device_ev.argtypes = [vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, dp, vp, vp, vp, i, vp, vp, vp]
+    lib.rtb200_mh_step_device_ev.argtypes = [vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, dp, vp, vp, vp, i, vp, vp, vp, i]
+    lib.rtb200_mh_moves_device_ex.restype = i
+    lib.rtb200_mh_moves_device_ex.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, dp, vp, vp, vp, i, vp, vp, i]
+    lib.rtb200_bd_step_device_ex.restype = i
+    lib.rtb200_bd_step_device_ex.argtypes = [vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, dp, dp, i, i,
+                                             vp, vp, vp, i, vp, vp, i]
     lib.rtb200_mh_moves_device.restype = i
     lib.rtb200_mh_moves_device.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, dp, vp, vp, vp, i, vp, vp]
     lib.rtb200_bd_step_device.restype = i

@@ -39,8 +39,15 @@ def cauchy_deviates(u):
     return torch.tan(math.pi * (u - 0.5))
 
 
+def move_deviates(u, iwhich, enos=False):
+    """The deviate PROPOSAL turns a uniform into: TAN(PI2*(ran_uni - 0.5)) (:1405, :1416), except
+    for a depth move (iwhich == 1) under ENOS = 1, which uses ran_uni itself (:1428)."""
+    c = cauchy_deviates(u)
+    return torch.where(iwhich == 1, u, c) if enos else c
+
+
 def mh_step_device(k, voro, logL, ivo, iwhich, cauchy, u_acc, beta, sigma, prior,
-                   src_offset, src_depth, tobs, accept=None, stream=None, beta_ready=None):
+                   src_offset, src_depth, tobs, accept=None, stream=None, beta_ready=None, enos=False):
     """One move of every chain, in place on `voro` and `logL`.
 
     k [B] i32, voro [B, 2, ldk] f64, logL/beta/sigma/cauchy/u_acc [B] f64, ivo/iwhich [B] i32
@@ -48,7 +55,9 @@ def mh_step_device(k, voro, logL, ivo, iwhich, cauchy, u_acc, beta, sigma, prior
     prior: 7 doubles on the host (prior_array).  Asynchronous on `stream` (default: torch's
     current stream).  `beta_ready` (a torch.cuda.Event, e.g. SwapRound.done) orders only the
     accept test behind it, so a swap round still running on another stream overlaps with the
-    proposal and likelihood kernels.  Returns accept [B] i32: 1 accepted, 0 rejected, -1 outside
+    proposal and likelihood kernels.  `enos` selects the parameter file's ENOS = 1 (even-numbered
+    order statistics prior, PROPOSAL :1418-1431): a depth move then takes the uniform itself in
+    `cauchy` (see `move_deviates`).  Returns accept [B] i32: 1 accepted, 0 rejected, -1 outside
     the bounds."""
     if not voro.is_cuda:
         raise ValueError("mh_step_device needs CUDA tensors (there is no CPU path)")
@@ -70,7 +79,7 @@ def mh_step_device(k, voro, logL, ivo, iwhich, cauchy, u_acc, beta, sigma, prior
         pr.ctypes.data_as(C.POINTER(C.c_double)), _ptr(src_offset, f64), _ptr(src_depth, f64),
         _ptr(tobs, f64), src_offset.numel(), _ptr(accept, i32),
         st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle(),
-        beta_ready.cuda_event if beta_ready is not None else None)
+        beta_ready.cuda_event if beta_ready is not None else None, 1 if enos else 0)
     _lib.check(rc)
     return accept
 
@@ -85,7 +94,7 @@ def poisson_pk(lam, kmin, kmax):
 
 
 def bd_step_device(k, voro, logL, u_k, idel, u_z, u_v, u_acc, beta, sigma, prior, pk, kmin, kmax,
-                   src_offset, src_depth, tobs, accept=None, stream=None):
+                   src_offset, src_depth, tobs, accept=None, stream=None, enos=False):
     """The birth/death move of every chain (rtb200_bd_step_device), in place on k, voro, logL.
     u_k/u_z/u_v/u_acc [B] f64 uniforms, idel [B] i32 (node a death removes, 2..k), pk: host array
     (poisson_pk) or None.  Returns accept [B] i32: 1 / 0 / -1 outside / 2 no move proposed."""
@@ -110,12 +119,12 @@ def bd_step_device(k, voro, logL, u_k, idel, u_z, u_v, u_acc, beta, sigma, prior
             raise ValueError("pk must hold kmax values")
         pkp = pka.ctypes.data_as(dp)
     st = stream if stream is not None else torch.cuda.current_stream(dev)
-    rc = _lib.load().rtb200_bd_step_device(
+    rc = _lib.load().rtb200_bd_step_device_ex(
         _ptr(k, i32), _ptr(voro, f64), _ptr(logL, f64), B, ldk, _ptr(u_k, f64), _ptr(idel, i32),
         _ptr(u_z, f64), _ptr(u_v, f64), _ptr(u_acc, f64), _ptr(beta, f64), _ptr(sigma, f64),
         pr.ctypes.data_as(dp), pkp, int(kmin), int(kmax), _ptr(src_offset, f64),
         _ptr(src_depth, f64), _ptr(tobs, f64), src_offset.numel(), _ptr(accept, i32),
-        st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle())
+        st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle(), 1 if enos else 0)
     _lib.check(rc)
     return accept
 
@@ -225,7 +234,7 @@ _moves_buffers = {}
 
 
 def mh_moves_device(k, voro, logL, pos, n_moves, beta, sigma, prior, src_offset, src_depth, tobs,
-                    generator=None):
+                    generator=None, enos=False):
     """n_moves moves in which EVERY chain makes its next move: chain b walks its own sweep
     (ivo, iwhich) = (1,2), (2,1), (2,2), ..., (k_b,1), (k_b,2) -- EXPLORE_MH_NOVARPAR's order,
     :725-731 -- and wraps around after its 2 k_b - 1 moves, so short chains do not idle while long
@@ -254,16 +263,18 @@ def mh_moves_device(k, voro, logL, pos, n_moves, beta, sigma, prior, src_offset,
     buf["iwhich"].copy_(j % 2 + 1)
     buf["u"].uniform_(generator=generator)
     torch.tan(math.pi * (buf["u"][0] - 0.5), out=buf["cauchy"])
+    if enos:
+        buf["cauchy"].copy_(torch.where(buf["iwhich"] == 1, buf["u"][0], buf["cauchy"]))
     pr = np.ascontiguousarray(prior, dtype=np.float64)
     if pr.size != 7:
         raise ValueError("prior must hold 7 doubles (see prior_array)")
     st = torch.cuda.current_stream(dev)
-    rc = _lib.load().rtb200_mh_moves_device(
+    rc = _lib.load().rtb200_mh_moves_device_ex(
         _ptr(k, i32), _ptr(voro, f64), _ptr(logL, f64), B, ldk, int(n_moves), _ptr(buf["ivo"], i32),
         _ptr(buf["iwhich"], i32), _ptr(buf["cauchy"], f64), _ptr(buf["u"][1], f64), _ptr(beta, f64),
         _ptr(sigma, f64), pr.ctypes.data_as(C.POINTER(C.c_double)), _ptr(src_offset, f64),
         _ptr(src_depth, f64), _ptr(tobs, f64), src_offset.numel(), _ptr(buf["accept"], i32),
-        st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle())
+        st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle(), 1 if enos else 0)
     _lib.check(rc)
     pos.copy_(((pos.to(torch.int64) + n_moves) % period).to(i32))
     return (buf["accept"] == 1).sum(dim=0)

@@ -903,8 +903,9 @@ int rtb200_dff_batch_device(const double *d_vels, const double *d_depths, const 
 
 namespace {
 
-rtb::MhPrior make_prior(const double *prior) {
+rtb::MhPrior make_prior(const double *prior, int enos = 0) {
     rtb::MhPrior pr;
+    pr.enos = enos ? 1 : 0;
     pr.scale[0] = prior[0]; pr.scale[1] = prior[1];
     pr.minlim[0] = prior[2]; pr.minlim[1] = prior[3];
     pr.maxlim[0] = prior[4]; pr.maxlim[1] = prior[5];
@@ -955,7 +956,7 @@ int rtb200_mh_step_device(const int *d_k, double *d_voro, double *d_logL, int B,
                           int *d_accept, void *stream) {
     return rtb200_mh_step_device_ev(d_k, d_voro, d_logL, B, ldk, d_ivo, d_iwhich, d_cauchy, d_uacc,
                                     d_beta, d_sigma, prior, d_src_offset, d_src_depth, d_tobs, NSrc,
-                                    d_accept, stream, nullptr);
+                                    d_accept, stream, nullptr, 0);
 }
 
 int rtb200_mh_step_device_ev(const int *d_k, double *d_voro, double *d_logL, int B, int ldk,
@@ -963,7 +964,7 @@ int rtb200_mh_step_device_ev(const int *d_k, double *d_voro, double *d_logL, int
                              const double *d_uacc, const double *d_beta, const double *d_sigma,
                              const double *prior, const double *d_src_offset,
                              const double *d_src_depth, const double *d_tobs, int NSrc,
-                             int *d_accept, void *stream, void *beta_ready_event) {
+                             int *d_accept, void *stream, void *beta_ready_event, int enos) {
     if (int rc = ensure_init()) return rc;
     g.err.clear();
     if (B <= 0) return 0;
@@ -974,10 +975,10 @@ int rtb200_mh_step_device_ev(const int *d_k, double *d_voro, double *d_logL, int
     TileCfg cfg;
     if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
     if (int rc = reserve_move_scratch(B, ldk, cfg)) return rc;
-    const rtb::MhPrior pr = make_prior(prior);
+    const rtb::MhPrior pr = make_prior(prior, enos);
     CK(rtb::launch_propose_voro(d_k, d_voro, B, ldk, d_ivo, d_iwhich, d_cauchy, pr,
                                 g.vels.as<double>(), g.depths.as<double>(), g.nl.as<int>(),
-                                g.vsorted.as<double>(), g.mh_out.as<int>(), st));
+                                g.vsorted.as<double>(), g.mh_lpr.as<double>(), g.mh_out.as<int>(), st));
     const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, d_sigma,
                                        next_sched());
     CK(cudaEventRecord(g.ev_k0[0], st));
@@ -986,7 +987,7 @@ int rtb200_mh_step_device_ev(const int *d_k, double *d_voro, double *d_logL, int
     // the proposal and its likelihood do not read beta; only the accept test does
     if (beta_ready_event) CK(cudaStreamWaitEvent(st, (cudaEvent_t)beta_ready_event, 0));
     CK(rtb::launch_mh_accept(d_k, d_voro, g.vsorted.as<double>(), d_logL, g.mh_ll.as<double>(),
-                             g.mh_out.as<int>(), d_uacc, d_beta, B, ldk, d_accept, st));
+                             g.mh_lpr.as<double>(), g.mh_out.as<int>(), d_uacc, d_beta, B, ldk, d_accept, st));
     g.launches += 3;
     g.last = cfg;
     if (!stream) {
@@ -1008,6 +1009,17 @@ int rtb200_mh_moves_device(const int *d_k, double *d_voro, double *d_logL, int B
                            const double *d_sigma, const double *prior, const double *d_src_offset,
                            const double *d_src_depth, const double *d_tobs, int NSrc,
                            int *d_accept, void *stream) {
+    return rtb200_mh_moves_device_ex(d_k, d_voro, d_logL, B, ldk, n_moves, d_ivo, d_iwhich, d_cauchy, d_uacc,
+                                     d_beta, d_sigma, prior, d_src_offset, d_src_depth, d_tobs, NSrc,
+                                     d_accept, stream, 0);
+}
+
+int rtb200_mh_moves_device_ex(const int *d_k, double *d_voro, double *d_logL, int B, int ldk,
+                              int n_moves, const int *d_ivo, const int *d_iwhich,
+                              const double *d_cauchy, const double *d_uacc, const double *d_beta,
+                              const double *d_sigma, const double *prior, const double *d_src_offset,
+                              const double *d_src_depth, const double *d_tobs, int NSrc,
+                              int *d_accept, void *stream, int enos) {
     if (int rc = ensure_init()) return rc;
     g.err.clear();
     if (B <= 0 || n_moves <= 0) return 0;
@@ -1026,7 +1038,8 @@ int rtb200_mh_moves_device(const int *d_k, double *d_voro, double *d_logL, int B
                                (size_t)g.vels.p, (size_t)g.depths.p, (size_t)g.nl.p,
                                (size_t)g.vsorted.p, (size_t)g.mh_ll.p, (size_t)g.mh_out.p,
                                (size_t)cfg.M, (size_t)cfg.grid, (size_t)cfg.variant, (size_t)g.opt_static_tiles,
-                               (size_t)g.chain_idxar, (size_t)g.chain_arpar};
+                               (size_t)g.chain_idxar, (size_t)g.chain_arpar, (size_t)(enos ? 1 : 0),
+                               (size_t)g.mh_lpr.p};
     {
         size_t bits;
         memcpy(&bits, &g.chain_armx, sizeof bits);
@@ -1040,7 +1053,7 @@ int rtb200_mh_moves_device(const int *d_k, double *d_voro, double *d_logL, int B
     if (!g.mv_exec || key != g.mv_key) {
         if (g.mv_exec) { cudaGraphExecDestroy(g.mv_exec); g.mv_exec = nullptr; }
         if (!g.s_cap) CK(cudaStreamCreateWithFlags(&g.s_cap, cudaStreamNonBlocking));
-        const rtb::MhPrior pr = make_prior(prior);
+        const rtb::MhPrior pr = make_prior(prior, enos);
         if (rtb::max_ctas_per_sm(cfg) < 1) return fail("batch kernel cannot be resident");   // sets the smem attribute
         CK(cudaStreamBeginCapture(g.s_cap, cudaStreamCaptureModeThreadLocal));
         cudaError_t e = cudaSuccess;
@@ -1048,14 +1061,15 @@ int rtb200_mh_moves_device(const int *d_k, double *d_voro, double *d_logL, int B
             const size_t o = (size_t)m * (size_t)B;
             e = rtb::launch_propose_voro(d_k, d_voro, B, ldk, d_ivo + o, d_iwhich + o, d_cauchy + o, pr,
                                          g.vels.as<double>(), g.depths.as<double>(), g.nl.as<int>(),
-                                         g.vsorted.as<double>(), g.mh_out.as<int>(), g.s_cap);
+                                         g.vsorted.as<double>(), g.mh_lpr.as<double>(), g.mh_out.as<int>(), g.s_cap);
             if (e != cudaSuccess) break;
             const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, d_sigma,
                                                g.opt_static_tiles ? nullptr : g.sched.as<int>() + 2 * (kSchedSlots + m));
             e = rtb::launch_batch(a, cfg, g.s_cap);
             if (e != cudaSuccess) break;
             e = rtb::launch_mh_accept(d_k, d_voro, g.vsorted.as<double>(), d_logL, g.mh_ll.as<double>(),
-                                      g.mh_out.as<int>(), d_uacc + o, d_beta, B, ldk, d_accept + o, g.s_cap);
+                                      g.mh_lpr.as<double>(), g.mh_out.as<int>(), d_uacc + o, d_beta, B, ldk,
+                                      d_accept + o, g.s_cap);
         }
         cudaGraph_t graph = nullptr;
         cudaError_t e2 = cudaStreamEndCapture(g.s_cap, &graph);
@@ -1079,6 +1093,17 @@ int rtb200_bd_step_device(int *d_k, double *d_voro, double *d_logL, int B, int l
                           const double *d_sigma, const double *prior, const double *pk, int kmin,
                           int kmax, const double *d_src_offset, const double *d_src_depth,
                           const double *d_tobs, int NSrc, int *d_accept, void *stream) {
+    return rtb200_bd_step_device_ex(d_k, d_voro, d_logL, B, ldk, d_uk, d_idel, d_uz, d_uv, d_uacc, d_beta,
+                                    d_sigma, prior, pk, kmin, kmax, d_src_offset, d_src_depth, d_tobs, NSrc,
+                                    d_accept, stream, 0);
+}
+
+int rtb200_bd_step_device_ex(int *d_k, double *d_voro, double *d_logL, int B, int ldk,
+                             const double *d_uk, const int *d_idel, const double *d_uz,
+                             const double *d_uv, const double *d_uacc, const double *d_beta,
+                             const double *d_sigma, const double *prior, const double *pk, int kmin,
+                             int kmax, const double *d_src_offset, const double *d_src_depth,
+                             const double *d_tobs, int NSrc, int *d_accept, void *stream, int enos) {
     if (int rc = ensure_init()) return rc;
     g.err.clear();
     if (B <= 0) return 0;
@@ -1090,7 +1115,7 @@ int rtb200_bd_step_device(int *d_k, double *d_voro, double *d_logL, int B, int l
     TileCfg cfg;
     if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
     if (int rc = reserve_move_scratch(B, ldk, cfg)) return rc;
-    const rtb::MhPrior pr = make_prior(prior);
+    const rtb::MhPrior pr = make_prior(prior, enos);
     rtb::BdPrior bd{};
     bd.kmin = kmin; bd.kmax = kmax; bd.use_pk = pk ? 1 : 0;
     for (int i = kmin; pk && i <= kmax; ++i) bd.logpk[i - 1] = std::log(pk[i - 1]);   // LOG(pk(i)), libm

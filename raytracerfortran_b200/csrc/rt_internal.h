@@ -73,6 +73,7 @@ struct MhPrior {
     double minlim[2];   // minlim(1:2)
     double maxlim[2];   // maxlim(1:2)
     double hmin;        // minimum layer thickness
+    int    enos;        // ENOS: 1 = even-numbered order statistics prior (Green 1995) in the moves
 };
 
 // Birth/death move: range of k and the Poisson prior on k (read_input.f90:70-81) as LOG(pk(i)).
@@ -88,10 +89,11 @@ cudaError_t launch_prep_voro(const int *k, const double *voro, int B, int ldk, d
 cudaError_t launch_propose_voro(const int *k, const double *voro, int B, int ldk, const int *ivo,
                                 const int *iwhich, const double *cauchy, const MhPrior &pr,
                                 double *vels, double *depths, int *keval, double *prop,
-                                int *outside, cudaStream_t st);
+                                double *logpr, int *outside, cudaStream_t st);
 cudaError_t launch_mh_accept(const int *k, double *voro, const double *prop, double *logL,
-                             const double *logL_prop, const int *outside, const double *u_acc,
-                             const double *beta, int B, int ldk, int *accept, cudaStream_t st);
+                             const double *logL_prop, const double *logpr, const int *outside,
+                             const double *u_acc, const double *beta, int B, int ldk, int *accept,
+                             cudaStream_t st);
 cudaError_t launch_propose_bd(const int *k, const double *voro, int B, int ldk, const double *u_k,
                               const int *idel, const double *u_z, const double *u_v,
                               const MhPrior &pr, const BdPrior &bd, double *vels, double *depths,

@@ -225,3 +225,64 @@ def test_ar_move_rules(cfg1):
     assert r["accept"][0] == 1 and r["idxar"][0] == 1 and r["arpar"][0] == 0.3 + ap[0] * 1.0
     assert step(1, 0.3, 0.2, 0.0, 5.0, 0.0)["accept"][0] == -1       # 1.0 > maxlimarRT
     assert step(1, 0.3, 0.2, 0.0, -6.0, 0.0)["accept"][0] == -1      # -0.54 < minlimarRT
+
+
+def test_enos_rules(cfg1):
+    """ENOS = 1 (even-numbered order statistics, Green 1995): PROPOSAL :1418-1431 draws the node
+    uniformly between its neighbours with logPr = LOG(zjp1-zp)+LOG(zp-zjm1)-LOG(zjp1-zj)-LOG(zj-zjm1);
+    DEATH_FULL :981-991 and BIRTH_FULL :1090-1098 add their order-statistics terms to logPr."""
+    voro, k = cfg1["voro"], cfg1["k"]
+    so, sd, tobs = cfg1["so"], cfg1["sd"], cfg1["tobs"]
+    ll0 = np.array([oracle.loglhood_rt(voro[0, 1, :k], voro[0, 0, 1:k], so, sd, tobs, 0.02)[0]])
+    pr, pk = chains.prior_array(), chains.poisson_pk(3.01, 1, 10)
+    hmx, hmin = pr[4], pr[6]
+    one = lambda x, dt=np.float64: np.array([x], dtype=dt)
+    oracle.set_enos(1)
+    try:
+        # ---- fixed-dimension depth move of node ivo = 3 (between nodes 2 and 4)
+        u = 0.3
+        zj, zjm1, zjp1 = voro[0, 0, 2], voro[0, 0, 1], voro[0, 0, 3]
+        zp = zjm1 + u * (zjp1 - zjm1)
+        r = _step(cfg1, voro, ll0, 3, 1, u, 0.0)
+        assert r["voro_prop"][0, 0, 2] == zp                          # :1428-1429
+        logPr = math.log(zjp1 - zp) + math.log(zp - zjm1) - math.log(zjp1 - zj) - math.log(zj - zjm1)
+        thr = math.exp(logPr + (r["logL_prop"][0] - ll0[0]))
+        for uu in (thr * 0.999, thr * 1.001):
+            if 0 < uu < 1:
+                assert _step(cfg1, voro, ll0, 3, 1, u, uu)["accept"][0] == (0 if uu >= thr else 1)
+        # the deepest node moves between its upper neighbour and hmx (:1423-1424)
+        r = _step(cfg1, voro, ll0, k, 1, 0.5, 0.0)
+        assert r["voro_prop"][0, 0, k - 1] == voro[0, 0, k - 2] + 0.5 * (hmx - voro[0, 0, k - 2])
+        # velocity moves are Cauchy steps whatever ENOS says (:1404-1405)
+        r = _step(cfg1, voro, ll0, 3, 2, 1e-3, 0.0)
+        assert r["voro"][0, 1, 2] == voro[0, 1, 2] + pr[1] * 1e-3
+
+        def bd(u_k, idel=2, u_z=0.5, u_v=0.5, u_acc=0.0, pk_=pk):
+            return oracle.bd_step_batch(one(k, np.int32), voro, ll0, one(u_k), one(idel, np.int32), one(u_z),
+                                        one(u_v), one(u_acc), one(1.0), one(0.02), pr, pk_, 1, 10, so, sd, tobs)
+        # ---- death of node idel = 3 (:941-947, :981-991)
+        zdel, zj, zjp1 = voro[0, 0, 2], voro[0, 0, 1], voro[0, 0, 3]
+        r = bd(0.9, idel=3)
+        enos = (2 * math.log(hmx - hmin) - math.log(2.0 * k * (2.0 * k + 1.0)) + math.log(zjp1 - zj)
+                - math.log(zdel - zj) - math.log(zjp1 - zdel))
+        for pk_, lp in ((pk, math.log(pk[k - 2]) - math.log(pk[k - 1]) + enos), (None, enos)):
+            thr = math.exp(lp + (r["logL_prop"][0] - ll0[0]))
+            for uu in (thr * 0.999, thr * 1.001):
+                if 0 < uu < 1:
+                    assert bd(0.9, idel=3, u_acc=uu, pk_=pk_)["accept"][0] == (0 if uu >= thr else 1)
+        # ---- birth (:1061-1073, :1090-1098)
+        u_z = 0.37
+        znew = (hmx - hmin) * u_z
+        r = bd(0.2, u_z=u_z, u_v=0.25)
+        zz = list(r["voro_prop"][0, 0, :k + 1])
+        i = zz.index(znew)
+        zj, zjp1 = zz[i - 1], (zz[i + 1] if i + 1 <= k else hmx)
+        enos = (math.log(2.0 * k + 2.0) + math.log(2.0 * k + 3.0) - 2 * math.log(hmx - hmin)
+                + math.log(znew - zj) + math.log(zjp1 - znew) - math.log(zjp1 - zj))
+        if r["accept"][0] != -1:
+            thr = math.exp(math.log(pk[k]) - math.log(pk[k - 1]) + enos + (r["logL_prop"][0] - ll0[0]))
+            for uu in (thr * 0.999, thr * 1.001):
+                if 0 < uu < 1:
+                    assert bd(0.2, u_z=u_z, u_v=0.25, u_acc=uu)["accept"][0] == (0 if uu >= thr else 1)
+    finally:
+        oracle.set_enos(0)

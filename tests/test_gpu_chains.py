@@ -468,3 +468,64 @@ def test_mcmc_step_device_with_ar():
             assert abs(got[b] - ref) <= 1e-11 * max(abs(ref), nsrc * abs(np.log(sg[b])))
         else:
             assert got[b] == ref
+
+
+def test_enos_moves_match_oracle():
+    """ENOS = 1 (order-statistics prior): fixed-dimension and birth/death moves against the oracle
+    over a trajectory -- same decisions, same node counts, bit-identical chain states."""
+    import torch
+    B, ldk, nsrc = 2000, 10, 20
+    kmin, kmax = 1, ldk
+    k, voro, so, sd, tobs, sigma, ll = _setup(B, ldk, nsrc, 71)
+    rng = np.random.default_rng(72)
+    prior, pk = chains.prior_array(), chains.poisson_pk(3.01, kmin, kmax)
+    beta = 1.0 / 1.4 ** rng.integers(0, 6, B)
+    tk, tv, tl, tb, tg, ts, td, to = _dev(k, voro, ll, beta, sigma, so, sd, tobs)
+    cur_k, cur_v, cur_l = k.copy(), voro, ll
+    seen_mh = {1: 0, 0: 0, -1: 0}
+    seen_bd = {1: 0, 0: 0, -1: 0, 2: 0}
+    oracle.set_enos(1)
+    try:
+        for step in range(10):
+            # a depth or velocity move of a random existing node
+            ivo = (1 + np.floor(rng.random(B) * cur_k)).astype(np.int32)
+            iwhich = rng.integers(1, 3, B).astype(np.int32)
+            uu = rng.random((2, B))
+            dev = np.where(iwhich == 1, uu[0], 0.05 * np.tan(np.pi * (uu[0] - 0.5)))
+            r = oracle.mh_step_batch(cur_k, cur_v, cur_l, ivo, iwhich, dev, uu[1], beta, sigma, prior, so, sd, tobs)
+            ti, tw, tc, tu = _dev(ivo, iwhich, dev, uu[1])
+            acc = chains.mh_step_device(tk, tv, tl, ti, tw, tc, tu, tb, tg, prior, ts, td, to, enos=True)
+            acc = acc.cpu().numpy()
+            assert np.array_equal(acc, r["accept"]), f"mh step {step}"
+            assert np.array_equal(tv.cpu().numpy().view(np.uint64), r["voro"].view(np.uint64)), f"mh step {step}"
+            cur_v, cur_l = r["voro"], r["logL"]
+            for c in seen_mh:
+                seen_mh[c] += int((acc == c).sum())
+            # birth / death
+            u = rng.random((4, B))
+            idel = (2 + np.floor(rng.random(B) * np.maximum(cur_k - 1, 1))).astype(np.int32)
+            r = oracle.bd_step_batch(cur_k, cur_v, cur_l, u[0], idel, u[1], u[2], u[3], beta, sigma, prior,
+                                     pk if step % 2 == 0 else None, kmin, kmax, so, sd, tobs)
+            t_u = _dev(u[0], u[1], u[2], u[3])
+            (t_idel,) = _dev(idel)
+            acc = chains.bd_step_device(tk, tv, tl, t_u[0], t_idel, t_u[1], t_u[2], t_u[3], tb, tg, prior,
+                                        pk if step % 2 == 0 else None, kmin, kmax, ts, td, to, enos=True)
+            acc = acc.cpu().numpy()
+            assert np.array_equal(acc, r["accept"]), f"bd step {step}"
+            assert np.array_equal(tk.cpu().numpy(), r["k"])
+            assert np.array_equal(tv.cpu().numpy().view(np.uint64), r["voro"].view(np.uint64)), f"bd step {step}"
+            cur_k, cur_v, cur_l = r["k"], r["voro"], r["logL"]
+            for c in seen_bd:
+                seen_bd[c] += int((acc == c).sum())
+    finally:
+        oracle.set_enos(0)
+    assert all(n > 50 for n in seen_mh.values()), seen_mh
+    assert all(n > 50 for n in seen_bd.values()), seen_bd
+    # and the ENOS depth move differs from the Cauchy one on the same deviates
+    ivo = np.minimum(2, cur_k).astype(np.int32)
+    iwhich = np.ones(B, dtype=np.int32)
+    uu = rng.random((2, B))
+    a = oracle.mh_step_batch(cur_k, cur_v, cur_l, ivo, iwhich, uu[0], uu[1], beta, sigma, prior, so, sd, tobs)
+    ti, tw, tc, tu = _dev(ivo, iwhich, uu[0], uu[1])
+    acc = chains.mh_step_device(tk, tv, tl, ti, tw, tc, tu, tb, tg, prior, ts, td, to, enos=False)
+    assert np.array_equal(acc.cpu().numpy(), a["accept"])
