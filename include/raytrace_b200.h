@@ -25,6 +25,8 @@
 #ifndef RAYTRACE_B200_H
 #define RAYTRACE_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -262,6 +264,32 @@ int rtb200_ar_step_device(const int *d_k, const double *d_voro, double *d_logL,
                           const double *d_uacc, const double *d_beta, const double *ar_prior,
                           const double *d_src_offset, const double *d_src_depth,
                           const double *d_tobs, int NSrc, int *d_accept, void *stream);
+
+/* One whole iteration of the sampler's worker loop (prjmh_temper_rf.f90:420-458) for B chains,
+ * n_iterations times, entirely on the device: the birth/death move (skipped when kmin == kmax),
+ * n_moves fixed-dimension moves in which every chain continues its own sweep (ivo, iwhich) =
+ * (1,2), (2,1), (2,2), ..., (k,1), (k,2) (:725-731) from d_pos[b], and the data-error move of
+ * EXPLORE_MH (:545-575).  Every random deviate is drawn by the library's Philox4x32-10 kernels
+ * (key = seed, counter = (chain, *d_counter, purpose)); the iteration is captured once as a CUDA
+ * graph and replayed, *d_counter advancing by one per iteration, so there is no host
+ * synchronisation and no per-move host work.  The chains' AR(1) state, if registered
+ * (rtb200_set_chain_ar), enters every likelihood; the AR move itself is not part of the graph.
+ *   d_k, d_voro, d_logL, d_sigma in/out; d_beta [B] read at every accept test (a swap round
+ *   between calls may rewrite it); d_pos [B] i32 in/out: position of each chain in its sweep
+ *   prior HOST [7], sd_prior HOST [3], pk HOST [kmax] or NULL, enos: as for the single moves
+ *   d_counter: one device uint64, in/out;  d_workspace: rtb200_mcmc_workspace_bytes(B, n_moves)
+ *   bytes holding the iteration's deviates and outcomes (layout: McmcWs in csrc/rt_internal.h,
+ *   mirrored by chains.mcmc_workspace_views);  d_tally [4][B] int64 or NULL, accumulated:
+ *   fixed-dimension moves accepted, evaluated, births/deaths accepted, sigma moves accepted */
+size_t rtb200_mcmc_workspace_bytes(int B, int n_moves);
+int rtb200_mcmc_iterations_device(int *d_k, double *d_voro, double *d_logL, double *d_sigma,
+                                  const double *d_beta, int *d_pos, int B, int ldk, int n_moves,
+                                  const double *prior, const double *sd_prior, const double *pk,
+                                  int kmin, int kmax, int enos, const double *d_src_offset,
+                                  const double *d_src_depth, const double *d_tobs, int NSrc,
+                                  unsigned long long seed, unsigned long long *d_counter,
+                                  void *d_workspace, long long *d_tally, int n_iterations,
+                                  void *stream);
 
 /* The parallel-tempering swap round (TEMPSWP_MH, prjmh_temper_rf.f90:1329-1384; master loop
  * :326-349) for n chains spread over the ranks of one job, decisions taken on the device.

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "libraytrace_b200
 EXPORTS = (
     "dff_", "dff7_", "tracerays_", "__raymod_MOD_tracerays", "raymod_mp_tracerays_", "raymod_tracerays_", "dff_batch", "loglhood_batch", "loglhood_batch_ar", "loglhood_batch_voro",
     "rtb200_dff_batch_device", "rtb200_mh_step_device", "rtb200_mh_step_device_ev", "rtb200_mh_moves_device", "rtb200_mh_moves_device_ex", "rtb200_bd_step_device_ex", "rtb200_bd_step_device", "rtb200_sd_step_device", "rtb200_ar_step_device", "rtb200_set_chain_ar",
-    "rtb200_swap_pack_device", "rtb200_swap_round_device",
+    "rtb200_swap_pack_device", "rtb200_swap_round_device", "rtb200_mcmc_workspace_bytes", "rtb200_mcmc_iterations_device",
     "rtb200_swap_pack_device", "rtb200_swap_round_device",
     "rtb200_init", "rtb200_shutdown", "rtb200_last_error", "rtb200_device_count",
     "rtb200_set_option", "rtb200_get_stat", "rtb200_fp64_peak_tflops", "rtb200_shard_range",
@@ -78,6 +78,11 @@ def load():
     lib.rtb200_ar_step_device.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, dp, vp, vp, vp, i, vp, vp]
     lib.rtb200_set_chain_ar.restype = i
     lib.rtb200_set_chain_ar.argtypes = [vp, vp, d]
+    lib.rtb200_mcmc_workspace_bytes.restype = C.c_size_t
+    lib.rtb200_mcmc_workspace_bytes.argtypes = [i, i]
+    lib.rtb200_mcmc_iterations_device.restype = i
+    lib.rtb200_mcmc_iterations_device.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, dp, dp, dp, i, i, i, vp, vp, vp, i,
+                                                  C.c_ulonglong, vp, vp, vp, i, vp]
     lib.rtb200_swap_pack_device.restype = i
     lib.rtb200_swap_pack_device.argtypes = [vp, vp, i, vp, vp]
     lib.rtb200_swap_round_device.restype = i

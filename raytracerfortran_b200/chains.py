@@ -296,8 +296,8 @@ def mcmc_step_device(k, voro, logL, sigma, beta, prior, sd_prior, pk, kmin, kmax
         return _mcmc_step(k, voro, logL, sigma, beta, prior, sd_prior, pk, kmin, kmax, src_offset, src_depth,
                           tobs, generator, ar)
     finally:
-        if ar is not None:
-            set_chain_ar()
+        if ar is not None:      # always unregister, without letting a stale error mask the real one
+            _lib.load().rtb200_set_chain_ar(None, None, 0.5)
 
 
 def _mcmc_step(k, voro, logL, sigma, beta, prior, sd_prior, pk, kmin, kmax, src_offset, src_depth, tobs,
@@ -337,3 +337,70 @@ def _mcmc_step(k, voro, logL, sigma, beta, prior, sd_prior, pk, kmin, kmax, src_
         out["ar"] = ar_step_device(k, voro, logL, sigma, ar[0], ar[1], ua[0].contiguous(), ua[1].contiguous(), ga,
                                    ua[2].contiguous(), beta, ar[2], src_offset, src_depth, tobs)
     return out
+
+
+def mcmc_workspace_views(workspace, B, n_moves):
+    """Named views into the workspace of rtb200_mcmc_iterations_device (a uint8 CUDA tensor of
+    rtb200_mcmc_workspace_bytes(B, n_moves) bytes; layout: McmcWs, csrc/rt_internal.h): the
+    iteration's deviates (u_k, u_z, u_v, u_acc_bd, u_gate, gauss, u_acc_sd [B]; dev, u_acc
+    [M, B]; idel [B]; ivo, iwhich [M, B]) and outcomes (acc_bd, acc_sd [B]; acc_mh [M, B])."""
+    M = int(n_moves)
+    nd = (7 + 2 * M) * B
+    d = workspace[:nd * 8].view(torch.float64)
+    i = workspace[nd * 8:nd * 8 + (3 + 3 * M) * B * 4].view(torch.int32)
+    names_d = ["u_k", "u_z", "u_v", "u_acc_bd", "u_gate", "gauss", "u_acc_sd"]
+    out = {n: d[j * B:(j + 1) * B] for j, n in enumerate(names_d)}
+    out["dev"] = d[7 * B:(7 + M) * B].view(M, B)
+    out["u_acc"] = d[(7 + M) * B:(7 + 2 * M) * B].view(M, B)
+    out["idel"], out["acc_bd"], out["acc_sd"] = i[:B], i[B:2 * B], i[2 * B:3 * B]
+    out["ivo"] = i[3 * B:(3 + M) * B].view(M, B)
+    out["iwhich"] = i[(3 + M) * B:(3 + 2 * M) * B].view(M, B)
+    out["acc_mh"] = i[(3 + 2 * M) * B:(3 + 3 * M) * B].view(M, B)
+    return out
+
+
+class McmcGraph:
+    """The sampler's worker loop (prjmh_temper_rf.f90:420-458) for B chains as one CUDA graph per
+    iteration, random numbers included (rtb200_mcmc_iterations_device): birth/death move, `n_moves`
+    fixed-dimension moves of every chain's own sweep, data-error move.  Owns the sweep positions,
+    the device iteration counter, the workspace and the tallies; `run(n)` replays the graph n
+    times without touching the host again."""
+
+    def __init__(self, k, voro, logL, sigma, beta, n_moves, prior, sd_prior, pk, kmin, kmax,
+                 src_offset, src_depth, tobs, seed=1, enos=False, counter0=0):
+        dev = voro.device
+        _ensure_device(dev.index if dev.index is not None else torch.cuda.current_device())
+        self.k, self.voro, self.logL, self.sigma, self.beta = k, voro, logL, sigma, beta
+        self.src = (src_offset, src_depth, tobs)
+        self.B, _, self.ldk = voro.shape
+        self.M = int(n_moves)
+        self.prior = np.ascontiguousarray(prior, dtype=np.float64)
+        self.sd_prior = np.ascontiguousarray(sd_prior, dtype=np.float64)
+        self.pk = None if pk is None else np.ascontiguousarray(pk, dtype=np.float64)
+        if self.prior.size != 7 or self.sd_prior.size != 3:
+            raise ValueError("prior must hold 7 doubles and sd_prior 3 (prior_array, sd_prior_array)")
+        if self.pk is not None and self.pk.size < kmax:
+            raise ValueError("pk must hold kmax values")
+        self.kmin, self.kmax, self.seed, self.enos = int(kmin), int(kmax), int(seed), bool(enos)
+        self.pos = torch.zeros(self.B, dtype=torch.int32, device=dev)
+        self.counter = torch.tensor([int(counter0)], dtype=torch.int64, device=dev)
+        nbytes = _lib.load().rtb200_mcmc_workspace_bytes(self.B, self.M)
+        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        self.tally = torch.zeros((4, self.B), dtype=torch.int64, device=dev)
+        self.views = mcmc_workspace_views(self.workspace, self.B, self.M)
+
+    def run(self, n_iterations=1, stream=None):
+        f64, i32 = torch.float64, torch.int32
+        dp = C.POINTER(C.c_double)
+        st = stream if stream is not None else torch.cuda.current_stream(self.voro.device)
+        so, sd, ob = self.src
+        rc = _lib.load().rtb200_mcmc_iterations_device(
+            _ptr(self.k, i32), _ptr(self.voro, f64), _ptr(self.logL, f64), _ptr(self.sigma, f64),
+            _ptr(self.beta, f64), _ptr(self.pos, i32), self.B, self.ldk, self.M,
+            self.prior.ctypes.data_as(dp), self.sd_prior.ctypes.data_as(dp),
+            None if self.pk is None else self.pk.ctypes.data_as(dp), self.kmin, self.kmax,
+            1 if self.enos else 0, _ptr(so, f64), _ptr(sd, f64), _ptr(ob, f64), so.numel(),
+            self.seed & 0xFFFFFFFFFFFFFFFF, self.counter.data_ptr(), self.workspace.data_ptr(),
+            self.tally.data_ptr(), int(n_iterations),
+            st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle())
+        _lib.check(rc)

@@ -29,7 +29,7 @@ using rtb::TileCfg;
 constexpr double kPi = 3.141592653589793238462643383279502884197;  // data_type.f90:5 (PI2)
 constexpr int    kMaxChunks = 64;
 constexpr int    kSchedSlots = 256;  // tile-scheduler counter pairs, one per launch in flight
-constexpr int    kGraphSlots = 512;  // further pairs owned by the kernel nodes of a captured graph
+constexpr int    kGraphSlots = 512;  // further pairs owned by the kernel nodes of a captured graph (two graphs)
 #ifndef RTB_SHALLOW_VARIANT
 #define RTB_SHALLOW_VARIANT 1
 #endif
@@ -65,11 +65,20 @@ struct Ctx {
     cudaEvent_t  ev_t0 = nullptr, ev_t1 = nullptr;
     DevBuf vels, depths, nl, off, dep, tobs, sigma, timeP, pout, logL, arena, voro, vsorted,
         idxar, arparb, sched, mh_ll, mh_out, mh_kp, mh_lpr;
+    // The scratch buffers below (vels ... mh_lpr) are shared by every entry.  Entries that return
+    // without synchronising (a caller stream was given) leave an event behind; any later entry that
+    // uses the scratch from another stream first makes that stream wait for it.
+    cudaEvent_t  ev_scratch = nullptr;
+    cudaStream_t scratch_stream = nullptr;
+    bool         scratch_pending = false;
     unsigned sched_seq = 0;        // launches take scheduler slots round robin
     bool     sched_dirty = false;  // a CUDA call failed: a kernel may have left counters behind
     // one cached CUDA graph of a run of MH moves (rtb200_mh_moves_device)
     cudaGraphExec_t     mv_exec = nullptr;
     std::vector<size_t> mv_key;
+    // one cached CUDA graph of a whole MCMC iteration (rtb200_mcmc_iterations_device)
+    cudaGraphExec_t     mc_exec = nullptr;
+    std::vector<size_t> mc_key;
     cudaStream_t        s_cap = nullptr;
     // IAR = 1: the chains' AR(1) state, used by every likelihood evaluation of the move entries
     const int    *chain_idxar = nullptr;
@@ -141,7 +150,8 @@ int ensure_init(int device = -1) {
     if (e != cudaSuccess || n == 0)
         return fail("no usable CUDA device (libraytrace_b200 has no CPU fallback)", e);
     g.device = device >= 0 ? device : pick_device();
-    if (g.device >= n) g.device = g.device % n;
+    if (g.device < 0) return fail("negative CUDA device index (RTB200_DEVICE / LOCAL_RANK)");
+    if (g.device >= n) g.device = g.device % n;      // more ranks than GPUs on this node: wrap
     CK(cudaSetDevice(g.device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, g.device));
@@ -162,8 +172,10 @@ int ensure_init(int device = -1) {
     }
     CK(cudaEventCreate(&g.ev_t0));
     CK(cudaEventCreate(&g.ev_t1));
-    CK(g.sched.reserve((kSchedSlots + kGraphSlots) * 2 * sizeof(int)));
-    CK(cudaMemset(g.sched.p, 0, (kSchedSlots + kGraphSlots) * 2 * sizeof(int)));
+    CK(cudaEventCreateWithFlags(&g.ev_scratch, cudaEventDisableTiming));
+    g.scratch_pending = false;
+    CK(g.sched.reserve((kSchedSlots + 2 * kGraphSlots) * 2 * sizeof(int)));
+    CK(cudaMemset(g.sched.p, 0, (kSchedSlots + 2 * kGraphSlots) * 2 * sizeof(int)));
     g.ok = true;
     g.err.clear();
     return 0;
@@ -171,12 +183,29 @@ int ensure_init(int device = -1) {
 
 int even_up(int x) { return (x + 1) & ~1; }
 
+// Order this stream behind the last asynchronous user of the shared scratch (see Ctx).
+int scratch_acquire(cudaStream_t st) {
+    if (g.scratch_pending && g.scratch_stream != st) CK(cudaStreamWaitEvent(st, g.ev_scratch, 0));
+    return 0;
+}
+// An entry has queued work on the scratch in `st`; `synced`: it has also waited for it.
+int scratch_release(cudaStream_t st, bool synced) {
+    if (synced) {
+        if (g.scratch_stream == st) g.scratch_pending = false;
+        return 0;
+    }
+    CK(cudaEventRecord(g.ev_scratch, st));
+    g.scratch_stream = st;
+    g.scratch_pending = true;
+    return 0;
+}
+
 // Counter pair for one launch's dynamic tile scheduling (the kernel leaves it zeroed).
 int *next_sched() {
     if (g.opt_static_tiles) return nullptr;
     if (g.sched_dirty) {
         cudaDeviceSynchronize();
-        if (cudaMemset(g.sched.p, 0, (kSchedSlots + kGraphSlots) * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+        if (cudaMemset(g.sched.p, 0, (kSchedSlots + 2 * kGraphSlots) * 2 * sizeof(int)) != cudaSuccess) return nullptr;
         g.sched_dirty = false;
     }
     return g.sched.as<int>() + 2 * (g.sched_seq++ % kSchedSlots);
@@ -480,6 +509,11 @@ int run_host(const HostCall &h) {
         CK(g.arparb.reserve(B * 8));
     }
 
+    if (g.scratch_pending) {       // an asynchronous device-path call may still be reading the scratch
+        CK(cudaStreamWaitEvent(g.s_h2d, g.ev_scratch, 0));
+        CK(cudaStreamWaitEvent(g.s_comp, g.ev_scratch, 0));
+        CK(cudaStreamWaitEvent(g.s_comp2, g.ev_scratch, 0));
+    }
     CK(cudaEventRecord(g.ev_t0, g.s_h2d));
     CK(cudaMemcpyAsync(g.off.p, h.off, S * 8, cudaMemcpyHostToDevice, g.s_h2d));
     CK(cudaMemcpyAsync(g.dep.p, h.dep, S * 8, cudaMemcpyHostToDevice, g.s_h2d));
@@ -708,8 +742,22 @@ void write_rays_dat(const double *vels, const double *depths, int NL, const doub
     fclose(fh);
 }
 
+// The reference opens rays.dat with status='REPLACE' on every call (subroutineR-quiet.f90:432-433,
+// :481-482), so after a call with keep_delta <= 0 the file is empty.  Doing that on every call
+// would put a file open/close on the latency path; it is done when it is observable: on the first
+// call of the process if the file exists, and after a call that wrote ray geometry.
+bool g_rays_dirty = true;
+
 void dff_impl(const double *vels, const double *depths, int NL, const double *off,
               const double *dep, int nsrc, double *timeP, int keep_delta) {
+    if (keep_delta <= 0 && g_rays_dirty) {
+        if (FILE *fh = fopen("rays.dat", "r")) {
+            fclose(fh);
+            if ((fh = fopen("rays.dat", "w"))) fclose(fh);
+        }
+        g_rays_dirty = false;
+    }
+    if (keep_delta > 0) g_rays_dirty = true;
     if (nsrc <= 0) return;
     std::vector<double> p;
     if (keep_delta > 0) p.resize((size_t)nsrc);
@@ -835,6 +883,7 @@ int loglhood_batch_voro(const int *k, const double *voro, const int *B, const in
     CK(g.sigma.reserve(Bz * 8)); CK(g.logL.reserve(Bz * 8));
     if (tpred) CK(g.timeP.reserve(Bz * S * 8));
     cudaStream_t st = g.s_comp;
+    if (int rc = scratch_acquire(st)) return rc;
     CK(cudaMemcpyAsync(g.voro.p, voro, Bz * 2 * ld * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(g.nl.p, k, Bz * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(g.off.p, src_offset, S * 8, cudaMemcpyHostToDevice, st));
@@ -975,6 +1024,7 @@ int rtb200_mh_step_device_ev(const int *d_k, double *d_voro, double *d_logL, int
     TileCfg cfg;
     if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
     if (int rc = reserve_move_scratch(B, ldk, cfg)) return rc;
+    if (int rc = scratch_acquire(st)) return rc;
     const rtb::MhPrior pr = make_prior(prior, enos);
     CK(rtb::launch_propose_voro(d_k, d_voro, B, ldk, d_ivo, d_iwhich, d_cauchy, pr,
                                 g.vels.as<double>(), g.depths.as<double>(), g.nl.as<int>(),
@@ -996,6 +1046,7 @@ int rtb200_mh_step_device_ev(const int *d_k, double *d_voro, double *d_logL, int
         CK(cudaEventElapsedTime(&ms, g.ev_k0[0], g.ev_k1[0]));
         g.kernel_ms = g.total_ms = ms;
     }
+    if (int rc = scratch_release(st, stream == nullptr)) return rc;
     return 0;
 }
 
@@ -1031,6 +1082,7 @@ int rtb200_mh_moves_device_ex(const int *d_k, double *d_voro, double *d_logL, in
     TileCfg cfg;
     if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
     if (int rc = reserve_move_scratch(B, ldk, cfg)) return rc;
+    if (int rc = scratch_acquire(st)) return rc;
     std::vector<size_t> key = {(size_t)d_k, (size_t)d_voro, (size_t)d_logL, (size_t)B, (size_t)ldk,
                                (size_t)n_moves, (size_t)d_ivo, (size_t)d_iwhich, (size_t)d_cauchy,
                                (size_t)d_uacc, (size_t)d_beta, (size_t)d_sigma, (size_t)d_src_offset,
@@ -1084,6 +1136,7 @@ int rtb200_mh_moves_device_ex(const int *d_k, double *d_voro, double *d_logL, in
     g.launches += 3LL * n_moves;
     g.last = cfg;
     if (!stream) CK(cudaStreamSynchronize(st));
+    if (int rc = scratch_release(st, stream == nullptr)) return rc;
     return 0;
 }
 
@@ -1115,6 +1168,7 @@ int rtb200_bd_step_device_ex(int *d_k, double *d_voro, double *d_logL, int B, in
     TileCfg cfg;
     if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
     if (int rc = reserve_move_scratch(B, ldk, cfg)) return rc;
+    if (int rc = scratch_acquire(st)) return rc;
     const rtb::MhPrior pr = make_prior(prior, enos);
     rtb::BdPrior bd{};
     bd.kmin = kmin; bd.kmax = kmax; bd.use_pk = pk ? 1 : 0;
@@ -1139,6 +1193,7 @@ int rtb200_bd_step_device_ex(int *d_k, double *d_voro, double *d_logL, int B, in
         CK(cudaEventElapsedTime(&ms, g.ev_k0[0], g.ev_k1[0]));
         g.kernel_ms = g.total_ms = ms;
     }
+    if (int rc = scratch_release(st, stream == nullptr)) return rc;
     return 0;
 }
 
@@ -1157,6 +1212,7 @@ int rtb200_sd_step_device(const int *d_k, const double *d_voro, double *d_logL, 
     TileCfg cfg;
     if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
     if (int rc = reserve_move_scratch(B, ldk, cfg)) return rc;
+    if (int rc = scratch_acquire(st)) return rc;
     CK(rtb::launch_propose_sd(d_k, d_voro, B, ldk, d_sigma, d_ugate, d_gauss, sd_prior[0],
                               sd_prior[1], sd_prior[2], g.vels.as<double>(), g.depths.as<double>(),
                               g.nl.as<int>(), g.mh_lpr.as<double>(), g.mh_out.as<int>(), st));
@@ -1175,10 +1231,12 @@ int rtb200_sd_step_device(const int *d_k, const double *d_voro, double *d_logL, 
         CK(cudaEventElapsedTime(&ms, g.ev_k0[0], g.ev_k1[0]));
         g.kernel_ms = g.total_ms = ms;
     }
+    if (int rc = scratch_release(st, stream == nullptr)) return rc;
     return 0;
 }
 
 int rtb200_set_chain_ar(const int *d_idxar, const double *d_arpar, double armx) {
+    g.err.clear();
     if ((d_idxar == nullptr) != (d_arpar == nullptr)) return fail("rtb200_set_chain_ar needs both arrays or neither");
     g.chain_idxar = d_idxar;
     g.chain_arpar = d_arpar;
@@ -1202,6 +1260,7 @@ int rtb200_ar_step_device(const int *d_k, const double *d_voro, double *d_logL,
     TileCfg cfg;
     if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
     if (int rc = reserve_move_scratch(B, ldk, cfg)) return rc;
+    if (int rc = scratch_acquire(st)) return rc;
     CK(g.idxar.reserve((size_t)B * 4));
     CK(g.arparb.reserve((size_t)B * 8));
     CK(rtb::launch_propose_ar(d_k, d_voro, B, ldk, d_idxar, d_arpar, d_uchoice, d_uprop, d_gauss,
@@ -1227,6 +1286,124 @@ int rtb200_ar_step_device(const int *d_k, const double *d_voro, double *d_logL,
         CK(cudaEventElapsedTime(&ms, g.ev_k0[0], g.ev_k1[0]));
         g.kernel_ms = g.total_ms = ms;
     }
+    if (int rc = scratch_release(st, stream == nullptr)) return rc;
+    return 0;
+}
+
+size_t rtb200_mcmc_workspace_bytes(int B, int n_moves) {
+    return (B > 0 && n_moves >= 0) ? rtb::mcmc_ws_bytes((size_t)B, (size_t)n_moves) : 0;
+}
+
+// One whole iteration of the sampler's worker loop (prjmh_temper_rf.f90:420-458) for B chains --
+// birth/death move, n_moves fixed-dimension moves of every chain's own sweep, data-error move --
+// with every random deviate drawn on the device, captured once as a CUDA graph and replayed
+// n_iterations times: no host synchronisation, no per-move host work.
+int rtb200_mcmc_iterations_device(int *d_k, double *d_voro, double *d_logL, double *d_sigma,
+                                  const double *d_beta, int *d_pos, int B, int ldk, int n_moves,
+                                  const double *prior, const double *sd_prior, const double *pk,
+                                  int kmin, int kmax, int enos, const double *d_src_offset,
+                                  const double *d_src_depth, const double *d_tobs, int NSrc,
+                                  unsigned long long seed, unsigned long long *d_counter,
+                                  void *d_workspace, long long *d_tally, int n_iterations,
+                                  void *stream) {
+    if (int rc = ensure_init()) return rc;
+    g.err.clear();
+    if (B <= 0 || n_iterations <= 0) return 0;
+    if (NSrc <= 0) return fail("rtb200_mcmc_iterations_device needs at least one source");
+    if (ldk < 1 || ldk > 64) return fail("rtb200_mcmc_iterations_device supports 1..64 nodes per state");
+    if (!prior || !sd_prior) return fail("rtb200_mcmc_iterations_device needs the prior and sd_prior arrays");
+    if (kmin < 1 || kmax < kmin || kmax > ldk) return fail("rtb200_mcmc_iterations_device needs 1 <= kmin <= kmax <= ldk");
+    if (n_moves < 0 || n_moves + 2 > kGraphSlots) return fail("rtb200_mcmc_iterations_device: at most 510 moves per iteration");
+    if (!d_counter || !d_workspace || !d_pos) return fail("rtb200_mcmc_iterations_device needs counter, workspace and pos");
+    cudaStream_t st = stream ? (cudaStream_t)stream : g.s_comp;
+    TileCfg cfg;
+    if (int rc = choose_cfg(B, ldk, ldk, NSrc, true, cfg)) return rc;
+    if (int rc = reserve_move_scratch(B, ldk, cfg)) return rc;
+    if (int rc = scratch_acquire(st)) return rc;
+    const rtb::McmcWs w = rtb::mcmc_ws_layout(d_workspace, (size_t)B, (size_t)n_moves);
+    std::vector<size_t> key = {(size_t)d_k, (size_t)d_voro, (size_t)d_logL, (size_t)d_sigma, (size_t)d_beta,
+                               (size_t)d_pos, (size_t)B, (size_t)ldk, (size_t)n_moves, (size_t)kmin, (size_t)kmax,
+                               (size_t)(enos ? 1 : 0), (size_t)d_src_offset, (size_t)d_src_depth, (size_t)d_tobs,
+                               (size_t)NSrc, (size_t)seed, (size_t)d_counter, (size_t)d_workspace, (size_t)d_tally,
+                               (size_t)g.vels.p, (size_t)g.depths.p, (size_t)g.nl.p, (size_t)g.vsorted.p,
+                               (size_t)g.mh_ll.p, (size_t)g.mh_out.p, (size_t)g.mh_kp.p, (size_t)g.mh_lpr.p,
+                               (size_t)cfg.M, (size_t)cfg.grid, (size_t)cfg.variant, (size_t)g.opt_static_tiles,
+                               (size_t)g.chain_idxar, (size_t)g.chain_arpar, (size_t)(pk ? 1 : 0)};
+    auto push_bits = [&](double x) { size_t bits; memcpy(&bits, &x, sizeof bits); key.push_back(bits); };
+    push_bits(g.chain_armx);
+    for (int i = 0; i < 7; ++i) push_bits(prior[i]);
+    for (int i = 0; i < 3; ++i) push_bits(sd_prior[i]);
+    for (int i = kmin; pk && i <= kmax; ++i) push_bits(pk[i - 1]);
+    if (!g.mc_exec || key != g.mc_key) {
+        if (g.mc_exec) { cudaGraphExecDestroy(g.mc_exec); g.mc_exec = nullptr; }
+        if (!g.s_cap) CK(cudaStreamCreateWithFlags(&g.s_cap, cudaStreamNonBlocking));
+        const rtb::MhPrior pr = make_prior(prior, enos);
+        rtb::BdPrior bd{};
+        bd.kmin = kmin; bd.kmax = kmax; bd.use_pk = pk ? 1 : 0;
+        for (int i = kmin; pk && i <= kmax; ++i) bd.logpk[i - 1] = std::log(pk[i - 1]);
+        if (rtb::max_ctas_per_sm(cfg) < 1) return fail("batch kernel cannot be resident");
+        int *slots = g.sched.as<int>() + 2 * (kSchedSlots + kGraphSlots);
+        auto slot = [&](int i) { return g.opt_static_tiles ? nullptr : slots + 2 * i; };
+        cudaStream_t sc = g.s_cap;
+        CK(cudaStreamBeginCapture(sc, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e = cudaSuccess;
+        auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; return e == cudaSuccess; };
+        // ---- deviates of the birth/death and data-error moves, then the birth/death move
+        ok(rtb::launch_mcmc_draw(d_counter, seed, d_k, B, w, sc));
+        if (e == cudaSuccess && kmin != kmax) {
+            ok(rtb::launch_propose_bd(d_k, d_voro, B, ldk, w.u_k, w.idel, w.u_z, w.u_v, pr, bd,
+                                      g.vels.as<double>(), g.depths.as<double>(), g.nl.as<int>(),
+                                      g.mh_kp.as<int>(), g.vsorted.as<double>(), g.mh_lpr.as<double>(),
+                                      g.mh_out.as<int>(), sc));
+            const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, d_sigma, slot(0));
+            if (e == cudaSuccess) ok(rtb::launch_batch(a, cfg, sc));
+            if (e == cudaSuccess)
+                ok(rtb::launch_bd_accept(d_k, d_voro, g.vsorted.as<double>(), g.mh_kp.as<int>(),
+                                         g.mh_lpr.as<double>(), d_logL, g.mh_ll.as<double>(),
+                                         g.mh_out.as<int>(), w.u_acc_bd, d_beta, B, ldk, w.acc_bd, sc));
+        }
+        // ---- every chain's next n_moves fixed-dimension moves (schedule from the node counts now)
+        if (e == cudaSuccess && n_moves > 0)
+            ok(rtb::launch_mcmc_sweep_draw(d_counter, seed, d_k, d_pos, B, n_moves, enos, w, sc));
+        for (int m = 0; m < n_moves && e == cudaSuccess; ++m) {
+            const size_t o = (size_t)m * (size_t)B;
+            ok(rtb::launch_propose_voro(d_k, d_voro, B, ldk, w.ivo + o, w.iwhich + o, w.dev + o, pr,
+                                        g.vels.as<double>(), g.depths.as<double>(), g.nl.as<int>(),
+                                        g.vsorted.as<double>(), g.mh_lpr.as<double>(), g.mh_out.as<int>(), sc));
+            const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, d_sigma, slot(1 + m));
+            if (e == cudaSuccess) ok(rtb::launch_batch(a, cfg, sc));
+            if (e == cudaSuccess)
+                ok(rtb::launch_mh_accept(d_k, d_voro, g.vsorted.as<double>(), d_logL, g.mh_ll.as<double>(),
+                                         g.mh_lpr.as<double>(), g.mh_out.as<int>(), w.u_acc + o, d_beta, B, ldk,
+                                         w.acc_mh + o, sc));
+        }
+        // ---- the data-error move
+        if (e == cudaSuccess) {
+            ok(rtb::launch_propose_sd(d_k, d_voro, B, ldk, d_sigma, w.u_gate, w.gauss, sd_prior[0], sd_prior[1],
+                                      sd_prior[2], g.vels.as<double>(), g.depths.as<double>(), g.nl.as<int>(),
+                                      g.mh_lpr.as<double>(), g.mh_out.as<int>(), sc));
+            const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc,
+                                               g.mh_lpr.as<double>(), slot(1 + n_moves));
+            if (e == cudaSuccess) ok(rtb::launch_batch(a, cfg, sc));
+            if (e == cudaSuccess)
+                ok(rtb::launch_sd_accept(d_sigma, g.mh_lpr.as<double>(), d_logL, g.mh_ll.as<double>(),
+                                         g.mh_out.as<int>(), w.u_acc_sd, d_beta, B, w.acc_sd, sc));
+        }
+        if (e == cudaSuccess) ok(rtb::launch_mcmc_finish(d_counter, d_k, d_pos, B, n_moves, w, d_tally, sc));
+        cudaGraph_t graph = nullptr;
+        cudaError_t e2 = cudaStreamEndCapture(sc, &graph);
+        if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail("capturing the MCMC iteration", e); }
+        if (e2 != cudaSuccess) return fail("cudaStreamEndCapture", e2);
+        e = cudaGraphInstantiate(&g.mc_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { g.mc_exec = nullptr; return fail("cudaGraphInstantiate", e); }
+        g.mc_key = key;
+    }
+    for (int it = 0; it < n_iterations; ++it) CK(cudaGraphLaunch(g.mc_exec, st));
+    g.launches += (long long)n_iterations * (3LL * n_moves + (kmin != kmax ? 3 : 0) + 3 + 2 + (n_moves > 0 ? 1 : 0));
+    g.last = cfg;
+    if (int rc = scratch_release(st, stream == nullptr)) return rc;
+    if (!stream) CK(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -1259,7 +1436,11 @@ int rtb200_swap_round_device(const double *d_all, int n, int lo, int n_local,
     return 0;
 }
 
-int rtb200_init(int device) { return ensure_init(device); }
+int rtb200_init(int device) {
+    const int rc = ensure_init(device);
+    if (rc == 0) g.err.clear();
+    return rc;
+}
 
 void rtb200_shutdown(void) {
     if (!g.inited || !g.ok) { g.inited = false; return; }
@@ -1285,11 +1466,17 @@ void rtb200_shutdown(void) {
     }
     cudaEventDestroy(g.ev_t0);
     cudaEventDestroy(g.ev_t1);
+    if (g.ev_scratch) cudaEventDestroy(g.ev_scratch);
+    g.ev_scratch = nullptr;
+    g.scratch_pending = false;
     cudaStreamDestroy(g.s_comp);
     cudaStreamDestroy(g.s_comp2);
     if (g.mv_exec) cudaGraphExecDestroy(g.mv_exec);
     g.mv_exec = nullptr;
     g.mv_key.clear();
+    if (g.mc_exec) cudaGraphExecDestroy(g.mc_exec);
+    g.mc_exec = nullptr;
+    g.mc_key.clear();
     g.chain_idxar = nullptr;
     g.chain_arpar = nullptr;
     if (g.s_cap) cudaStreamDestroy(g.s_cap);
@@ -1341,6 +1528,7 @@ double rtb200_get_stat(const char *name) {
 
 double rtb200_fp64_peak_tflops(int repeats) {
     if (ensure_init()) return std::numeric_limits<double>::quiet_NaN();
+    g.err.clear();
     double tf = 0.0;
     if (rtb::fp64_peak(&tf, repeats, g.s_comp) != cudaSuccess)
         return std::numeric_limits<double>::quiet_NaN();
@@ -1350,6 +1538,7 @@ double rtb200_fp64_peak_tflops(int repeats) {
 
 double rtb200_selftest_fast_division(double samples, unsigned long long seed) {
     if (ensure_init()) return -1.0;
+    g.err.clear();
     double bad = -1.0;
     if (rtb::fastpath_selftest(samples, seed, &bad, g.s_comp) != cudaSuccess) return -1.0;
     g.launches += 1;

@@ -83,14 +83,23 @@ def dff_batch(vels, depths, nlayers, src_offset, src_depth, tobs=None, sigma=Non
     nl_max = int(nl.max()) if B else 0
     if nl_max + 1 > v.shape[1] or nl_max > max(z.shape[1], 0):
         raise ValueError("nlayers exceeds the row length of vels / depths")
-    t = out_times if out_times is not None else (np.empty((B, nsrc)) if want_times else None)
-    p = out_p if out_p is not None else (np.empty((B, nsrc)) if want_p else None)
+    def _out(a, shape, name):
+        # the library writes prod(shape) doubles through this pointer: refuse anything else
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+                and a.flags["WRITEABLE"] and a.shape == shape):
+            raise ValueError(f"{name} must be a writable C-contiguous float64 array of shape {shape}")
+        return a
+
+    t = _out(out_times, (B, nsrc), "out_times") if out_times is not None else (np.empty((B, nsrc)) if want_times else None)
+    p = _out(out_p, (B, nsrc), "out_p") if out_p is not None else (np.empty((B, nsrc)) if want_p else None)
     ll = ob = sg = None
     if tobs is not None:
+        if sigma is None:
+            raise ValueError("sigma [B] is required with tobs (the fused likelihood)")
         ob, sg = _d(tobs), _d(sigma)
         if ob.size != nsrc or sg.size != B:
             raise ValueError("tobs must be [NSrc] and sigma [B]")
-        ll = out_logL if out_logL is not None else np.empty(B)
+        ll = _out(out_logL, (B,), "out_logL") if out_logL is not None else np.empty(B)
     rc = _lib.load().dff_batch(_p(v), _p(z), nl.ctypes.data_as(_IP), _ci(B), _ci(v.shape[1]),
                                _ci(z.shape[1]), _p(so), _p(sd), _ci(nsrc), _p(t), _p(ob), _p(sg),
                                _p(ll), _p(p))

@@ -529,3 +529,69 @@ def test_enos_moves_match_oracle():
     ti, tw, tc, tu = _dev(ivo, iwhich, uu[0], uu[1])
     acc = chains.mh_step_device(tk, tv, tl, ti, tw, tc, tu, tb, tg, prior, ts, td, to, enos=False)
     assert np.array_equal(acc.cpu().numpy(), a["accept"])
+
+
+@pytest.mark.parametrize("enos", [False, True])
+def test_mcmc_graph_iteration_matches_oracle(enos):
+    """rtb200_mcmc_iterations_device: a whole iteration (birth/death, every chain's next moves of
+    its own sweep, data-error move) as one CUDA graph with the deviates drawn on the device.  The
+    deviates are read back from the workspace and the oracle replays the iteration with them:
+    same outcomes of every move, same node counts, bit-identical states, iteration after iteration."""
+    import torch
+    B, ldk, nsrc, M = 1500, 10, 20, 7
+    kmin, kmax = 1, ldk
+    k, voro, so, sd, tobs, sigma, ll = _setup(B, ldk, nsrc, 91)
+    rng = np.random.default_rng(92)
+    prior, sd_prior, pk = chains.prior_array(), chains.sd_prior_array(), chains.poisson_pk(3.01, kmin, kmax)
+    beta = 1.0 / 1.4 ** rng.integers(0, 6, B)
+    tk, tv, tl, tg, tb, ts, td, to = _dev(k, voro, ll, sigma, beta, so, sd, tobs)
+    g = chains.McmcGraph(tk, tv, tl, tg, tb, M, prior, sd_prior, pk, kmin, kmax, ts, td, to, seed=5, enos=enos)
+    cur_k, cur_v, cur_l, cur_s = k.copy(), voro, ll, sigma.copy()
+    pos = np.zeros(B, dtype=np.int64)
+    first_u = None
+    oracle.set_enos(1 if enos else 0)
+    try:
+        for it in range(3):
+            g.run(1)
+            torch.cuda.synchronize()
+            w = {n: t.cpu().numpy().copy() for n, t in g.views.items()}
+            for n in ("u_k", "u_z", "u_v", "u_acc_bd", "u_gate", "u_acc_sd", "u_acc"):
+                assert ((w[n] >= 0) & (w[n] < 1)).all(), n
+            assert abs(w["gauss"].mean()) < 0.1 and 0.9 < w["gauss"].std() < 1.1
+            if first_u is None:
+                first_u = w["u_k"].copy()
+            else:
+                assert not np.array_equal(first_u, w["u_k"])         # the counter moved the stream on
+            assert ((w["idel"] >= 2) & (w["idel"] <= np.maximum(cur_k, 2))).all()
+            r = oracle.bd_step_batch(cur_k, cur_v, cur_l, w["u_k"], w["idel"], w["u_z"], w["u_v"], w["u_acc_bd"],
+                                     beta, cur_s, prior, pk, kmin, kmax, so, sd, tobs)
+            assert np.array_equal(w["acc_bd"], r["accept"]), f"bd, iteration {it}"
+            cur_k, cur_v, cur_l = r["k"], r["voro"], r["logL"]
+            period = np.maximum(2 * cur_k.astype(np.int64) - 1, 1)
+            for m in range(M):
+                j = (pos + m) % period + 1
+                assert np.array_equal(w["ivo"][m], j // 2 + 1) and np.array_equal(w["iwhich"][m], j % 2 + 1)
+                r = oracle.mh_step_batch(cur_k, cur_v, cur_l, w["ivo"][m], w["iwhich"][m], w["dev"][m], w["u_acc"][m],
+                                         beta, cur_s, prior, so, sd, tobs)
+                assert np.array_equal(w["acc_mh"][m], r["accept"]), f"move {m}, iteration {it}"
+                cur_v, cur_l = r["voro"], r["logL"]
+            pos = (pos + M) % period
+            r = oracle.sd_step_batch(cur_k, cur_v, cur_l, cur_s, w["u_gate"], w["gauss"], w["u_acc_sd"], beta,
+                                     sd_prior, so, sd, tobs)
+            assert np.array_equal(w["acc_sd"], r["accept"]), f"sd, iteration {it}"
+            cur_l, cur_s = r["logL"], r["sigma"]
+            assert np.array_equal(tk.cpu().numpy(), cur_k)
+            assert np.array_equal(tv.cpu().numpy().view(np.uint64), cur_v.view(np.uint64)), f"iteration {it}"
+            assert np.array_equal(tg.cpu().numpy().view(np.uint64), cur_s.view(np.uint64))
+            assert np.array_equal(g.pos.cpu().numpy(), pos)
+    finally:
+        oracle.set_enos(0)
+    assert int(g.counter.item()) == 3
+    tally = g.tally.cpu().numpy()
+    assert tally[1].sum() > 0 and 0 < tally[0].sum() < tally[1].sum() and tally[2].sum() > 0 and tally[3].sum() > 0
+    # many iterations back to back, no host work in between
+    g.run(20)
+    torch.cuda.synchronize()
+    assert int(g.counter.item()) == 23
+    kk = tk.cpu().numpy()
+    assert kk.min() >= kmin and kk.max() <= kmax and np.isfinite(tl.cpu().numpy()).all()
