@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--moves", type=int, default=20, help="MH moves per chain between swap rounds")
     ap.add_argument("--replicas", type=int, default=8, help="tempering replicas per GPU")
     ap.add_argument("--chains", type=int, default=1024, help="independent chains per replica")
+    ap.add_argument("--eager", action="store_true", help="round 1's path: host-side deviates, one graph per run of moves")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -67,6 +68,19 @@ def main():
 
     pk = chains.poisson_pk(3.01, 1, ldk)
 
+    sd_prior = chains.sd_prior_array()
+    graph = chains.McmcGraph(tk, tv, tl, tg, beta, M, prior, sd_prior, pk, 1, ldk, ts, td, to, seed=2026 + rank)
+    swapper = tempering.SwapRound(B, dev)
+
+    def sweep_graph(i):
+        # one captured iteration (birth/death + M moves of every chain's own sweep + sigma move, all
+        # deviates drawn on the device), then the swap round on a side stream; the next iteration's
+        # graph waits for the new betas (the graph reads beta in its first accept test)
+        swapper.wait()
+        graph.run(1)
+        swapper.launch(tl, beta, 2026, i)
+        return None
+
     def sweep(i):
         # the birth/death move that opens EXPLORE_MH_NOVARPAR (:658-710), then the fixed-k moves
         u = torch.rand((5, B), dtype=torch.float64, device=dev, generator=gen)
@@ -79,18 +93,28 @@ def main():
         beta.copy_(nb)          # same buffer every round: the captured graph of moves stays valid
         return acc
 
-    sweep(0)
+    use_graph = not args.eager
+    swapper.launch(tl, beta, 2026, 0)
+    (sweep_graph if use_graph else sweep)(0)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     launches0 = rt.get_stat("launches")
+    graph.tally.zero_()
     t0 = time.perf_counter()
     acc_t = 0
     for i in range(args.sweeps):
-        acc_t = acc_t + sweep(1 + i).sum()
+        if use_graph:
+            sweep_graph(1 + i)
+        else:
+            acc_t = acc_t + sweep(1 + i).sum()
+    if use_graph:
+        swapper.wait()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    moves = B * (M + 1) * args.sweeps
+    if use_graph:
+        acc_t = graph.tally[0].sum() + graph.tally[2].sum()
+    moves = B * (M + (2 if use_graph else 1)) * args.sweeps
     tt = torch.tensor([wall, float(moves), float(acc_t.item())], dtype=torch.float64, device=dev)
     if world > 1:
         mx = tt.clone()
@@ -105,6 +129,8 @@ def main():
             "rounds": args.sweeps, "moves_per_round": M, "seconds": wall, "mh_moves": moves_all,
             "mh_moves_per_s": moves_all / wall, "evals_per_s": moves_all * nsrc / wall,
             "acceptance": acc_all / moves_all,
+            "mode": "eager (torch deviates, graph of the fixed-k moves only)" if args.eager else
+                    "one CUDA graph per iteration, deviates drawn on the device, swap round on a side stream",
             "kernel_launches_per_move": 3, "birth_death_moves_per_round": 1, "final_mean_k": float(tk.double().mean().item()), "library_launches": rt.get_stat("launches") - launches0,
             "max_k": int(k.max())}))
     if world > 1:

@@ -12,12 +12,15 @@ def find(pat, start=0):
         if pat in cu[i]: return i + 1
     raise SystemExit(f"marker not found: {pat}")
 kstart = find("rt_batch_kernel(const BatchArgs a")
+v4 = find("// ---- variant 4: the solve as level-synchronous", kstart)     # variant 4's block sits between variant 0 and 1
+v1 = find("constexpr bool kDeep = (VARIANT == 3);", v4)
 marks = [("kernel prologue", kstart), ("A stage+tables", find("// ---------------- A:", kstart)),
          ("B per-ray setup", find("// ---------------- B:", kstart)), ("sort", find("// ---------------- counting sort", kstart)),
-         ("C variant0", find("// ---------------- C: solve", kstart)), ("C refill", find("// ---- refill idle lanes", kstart)),
-         ("C eval loop ctl", find("// ---- f and f' at x", kstart)), ("C transition", find("// ---- advance the ray", kstart)),
-         ("C' travel times", find("// ---- travel times at the final p", kstart)), ("D outputs", find("// ---------------- D:", kstart)),
-         ("end", len(cu) + 1)]
+         ("C variant0", find("// ---------------- C: solve", kstart)), ("C variant4 (queues)", v4),
+         ("C refill", find("// ---- refill idle lanes", v1)),
+         ("C eval loop ctl", find("// ---- f and f' at x", v1)), ("C transition", find("// ---- advance the ray", v1)),
+         ("C' travel times", find("// ---- travel times at the final p", v1)), ("D outputs", find("// ---------------- D:", v1)),
+         ("end", find("// \"next\" row N1: INTERPLAYER_novar", v1))]
 helpers = [("fp64 prims (dmul..dsqrt builtins)", find("double dmul(double a"), find("double dsqrt(double a") + 1),
            ("eval_time/eval_ffp (builtin path)", find("struct Tables"), find("// rsqrt-seeded square root")),
            ("sqrt_rsqrt", find("double sqrt_rsqrt("), find("double div_seeded(")),

@@ -227,7 +227,7 @@ int choose_cfg(int B, int ldv, int ldz, int nsrc, bool aligned, TileCfg &c) {
     c.logl_shuffle = g.opt_logl_shuffle;
     const int rays_target = c.threads * 8;
     int M = g.opt_tile_models > 0 ? g.opt_tile_models : std::max(2, rays_target / c.SC);
-    M = even_up(std::min(M, even_up(B)));
+    M = g.opt_tile_models > 0 ? std::max(1, std::min(M, B)) : even_up(std::min(M, even_up(B)));
     const int want_ctas = g.opt_ctas > 0 ? g.opt_ctas : (c.variant == 3 ? 2 : c.variant == 4 ? 4 : 3);
     const size_t budget  = (size_t)g.smem_optin;
     const size_t per_cta = std::min<size_t>(budget, (size_t)(227 * 1024) / want_ctas - 1024);
@@ -247,7 +247,10 @@ int choose_cfg(int B, int ldv, int ldz, int nsrc, bool aligned, TileCfg &c) {
     }
     int occ = rtb::max_ctas_per_sm(c);
     if (occ < 1) return fail("batch kernel cannot be resident with this tile geometry");
-    // few models: shrink the tile so one wave of CTAs covers the batch
+    // few models: shrink the tile so one wave of CTAs covers the batch.  (Measured on 4096 and
+    // 8192 trans-dimensional states x 256 sources: tiles of 2..7 or 12 models are no faster than
+    // this rule's 8 -- such a batch is one or two waves of latency-bound tiles, not a queue of
+    // rounds, so neither finer tiles nor "rounds x tile cost" tuning helps; profiles/r02_*.)
     if (g.opt_tile_models <= 0 && (B + c.M - 1) / c.M < g.sms * occ) {
         const int slots = g.sms * occ;
         const int m2 = std::max(2, even_up((B + slots - 1) / slots));
@@ -1498,7 +1501,7 @@ int rtb200_set_option(const char *name, double value) {
     const int v = (int)value;
     if (!strcmp(name, "variant")) g.opt_variant = v < 0 ? -1 : v;
     else if (!strcmp(name, "threads")) g.opt_threads = v;
-    else if (!strcmp(name, "tile_models")) g.opt_tile_models = v > 0 ? even_up(v) : 0;
+    else if (!strcmp(name, "tile_models")) g.opt_tile_models = v > 0 ? v : 0;
     else if (!strcmp(name, "tile_sources")) g.opt_tile_sources = v;
     else if (!strcmp(name, "chunk_models")) g.opt_chunk_models = v;
     else if (!strcmp(name, "ctas_per_sm")) g.opt_ctas = v;
