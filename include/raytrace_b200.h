@@ -327,7 +327,10 @@ int         rtb200_device_count(void);        /* 0 without a driver / device    
  *          "stage_pageable" (-1 default: large pageable host inputs are copied by a few host
  *          threads into a pinned ring so that H2D stays asynchronous; 0 never; 1 always);
  *          "latency_path" (1 default: a one-model call without likelihood -- dff_, TraceRays --
- *          runs the one-warp-per-ray kernel on mapped pinned memory; 0: the batch kernel) */
+ *          runs the one-warp-per-ray kernel on mapped pinned memory; 0: the batch kernel);
+ *          "stable_lognorm" (0 default: LOG(1/(2 PI2)**(N/2)) as loglhood.f90:194 writes it, which
+ *          is -Inf for N >= 772 sources; 1: the same constant as -(N/2) LOG(2 PI2), finite for any
+ *          N -- a deviation from the reference, for likelihoods over more than 771 data) */
 int         rtb200_set_option(const char *name, double value);
 /* stats of the last batched call: "kernel_ms", "total_ms", "launches" (cumulative),
  *          "tile_models", "tile_sources", "smem_bytes", "grid", "threads", "ctas_per_sm" */

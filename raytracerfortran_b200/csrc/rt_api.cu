@@ -97,6 +97,7 @@ struct Ctx {
     void  *lat = nullptr;
     size_t lat_cap = 0;
     int opt_latency = 1;           // 1: one-model calls take the latency kernel; 0: the batch kernel
+    int opt_stable_lognorm = 0;    // 1: log-likelihood constant as -(N/2) log(2 pi) (finite for N >= 772)
     // options (<= 0: automatic)
     int opt_variant = -1, opt_threads = 0, opt_tile_models = 0, opt_tile_sources = 0,
         opt_chunk_models = 0, opt_ctas = 0, opt_logl_shuffle = 0, opt_comp_streams = 0, opt_static_tiles = 0;
@@ -268,7 +269,11 @@ int choose_cfg(int B, int ldv, int ldz, int nsrc, bool aligned, TileCfg &c) {
 
 double log_norm_const(int nsrc) {
     // LOG(1._RP/(2._RP*PI2)**(REAL(NDAT_RT,RP)/2._RP))     loglhood.f90:194
+    // For NDAT_RT >= 772 the power overflows, 1/Inf = 0 and the reference's logL is -Inf for every
+    // model; that is reproduced by default.  Option "stable_lognorm" (a documented deviation, off
+    // by default) evaluates the same constant as -(N/2) LOG(2 PI2), which stays finite.
     const double n = (double)nsrc;
+    if (g.opt_stable_lognorm) return -(n / 2.0) * std::log(2.0 * kPi);
     return std::log(1.0 / std::pow(2.0 * kPi, n / 2.0));
 }
 
@@ -1510,6 +1515,7 @@ int rtb200_set_option(const char *name, double value) {
     else if (!strcmp(name, "logl_shuffle")) g.opt_logl_shuffle = v > 0 ? 1 : 0;
     else if (!strcmp(name, "stage_pageable")) g.opt_stage = v < 0 ? -1 : (v > 0 ? 1 : 0);
     else if (!strcmp(name, "latency_path")) g.opt_latency = v == 0 ? 0 : 1;
+    else if (!strcmp(name, "stable_lognorm")) g.opt_stable_lognorm = v > 0 ? 1 : 0;
     else return -1;
     return 0;
 }
