@@ -83,6 +83,18 @@ def test_config5_stress_slice():
     assert np.array_equal(got["logL"][pick], ref["logL"])
     only_ll = rt.dff_batch(v, z, nl, so, sd, tobs=tobs, sigma=sigma, want_times=False)
     assert np.array_equal(only_ll["logL"], got["logL"])
+    assert np.all(np.isneginf(got["logL"]))
+    # opt-in deviation: the same constant as -(N/2) log(2 pi) keeps logL finite for N >= 772
+    rt.set_option("stable_lognorm", 1)
+    try:
+        st = rt.dff_batch(v[pick], z[pick], nl[pick], so, sd, tobs=tobs, sigma=sigma[pick], want_times=True)
+    finally:
+        rt.set_option("stable_lognorm", 0)
+    assert np.array_equal(bits(st["timeP"]), bits(ref["timeP"]))
+    res = tobs[None, :] - ref["timeP"]
+    sg = sigma[pick]
+    want = -(nsrc / 2.0) * np.log(2 * np.pi) - ((res * res).sum(axis=1) / (2 * sg * sg) + nsrc * np.log(sg))
+    assert np.all(np.isfinite(st["logL"])) and np.allclose(st["logL"], want, rtol=1e-12, atol=0)
 
 
 def test_next_row_n1_device_side_interplayer_novar():
