@@ -94,6 +94,23 @@ int dff_batch(const double *vels, const double *depths, const int *nlayers,
               double *timeP, const double *tobs, const double *sigma,
               double *logL, double *p_out);
 
+/* dff_batch for callers that cannot see a C return value: R's .C() and .Fortran() discard it and
+ * pass every argument as a pointer.  Same arguments, plus *status = what dff_batch returns
+ * (0 = ok; the message is rtb200_last_error()).  Exported as dff_batch_status (R: .C) and
+ * dff_batch_status_ (R: .Fortran; Fortran without bind(C)).  R cannot pass NULL for an optional
+ * array: pass a length-0 vector and the matching want flag = 0 --
+ *   want[0] timeP, want[1] logL (then tobs and sigma are read), want[2] p_out. */
+void dff_batch_status(const double *vels, const double *depths, const int *nlayers, const int *B,
+                      const int *ldv, const int *ldz, const double *src_offset,
+                      const double *src_depth, const int *NSrc, double *timeP, const double *tobs,
+                      const double *sigma, double *logL, double *p_out, const int *want,
+                      int *status);
+void dff_batch_status_(const double *vels, const double *depths, const int *nlayers, const int *B,
+                       const int *ldv, const int *ldz, const double *src_offset,
+                       const double *src_depth, const int *NSrc, double *timeP, const double *tobs,
+                       const double *sigma, double *logL, double *p_out, const int *want,
+                       int *status);
+
 /* LOGLHOOD / LOGLHOOD_RT (loglhood.f90:3-32,35-211) over B chain states, with the model
  * mapping of :127-146: state b has k[b] Voronoi nodes, vp[b][0..k-1] = voro(1:k,2),
  * ziface[b][0..k-2] = ziface(1:k-1); k == 1 becomes two equal velocities over one fake

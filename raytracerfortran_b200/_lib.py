@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "libraytrace_b200
 
 # every symbol include/raytrace_b200.h declares
 EXPORTS = (
-    "dff_", "dff7_", "tracerays_", "__raymod_MOD_tracerays", "raymod_mp_tracerays_", "raymod_tracerays_", "dff_batch", "loglhood_batch", "loglhood_batch_ar", "loglhood_batch_voro",
+    "dff_", "dff7_", "tracerays_", "__raymod_MOD_tracerays", "raymod_mp_tracerays_", "raymod_tracerays_", "dff_batch", "dff_batch_status", "dff_batch_status_", "loglhood_batch", "loglhood_batch_ar", "loglhood_batch_voro",
     "rtb200_dff_batch_device", "rtb200_mh_step_device", "rtb200_mh_step_device_ev", "rtb200_mh_moves_device", "rtb200_mh_moves_device_ex", "rtb200_bd_step_device_ex", "rtb200_bd_step_device", "rtb200_sd_step_device", "rtb200_ar_step_device", "rtb200_set_chain_ar",
     "rtb200_swap_pack_device", "rtb200_swap_round_device", "rtb200_mcmc_workspace_bytes", "rtb200_mcmc_iterations_device",
     "rtb200_swap_pack_device", "rtb200_swap_round_device",
@@ -50,6 +50,9 @@ def load():
     lib.dff7_.argtypes = [dp, dp, ip, dp, dp, ip, dp]
     lib.dff_batch.restype = i
     lib.dff_batch.argtypes = [dp, dp, ip, ip, ip, ip, dp, dp, ip, dp, dp, dp, dp, dp]
+    for nm in ("dff_batch_status", "dff_batch_status_"):
+        getattr(lib, nm).restype = None
+        getattr(lib, nm).argtypes = [dp, dp, ip, ip, ip, ip, dp, dp, ip, dp, dp, dp, dp, dp, ip, ip]
     lib.loglhood_batch.restype = i
     lib.loglhood_batch.argtypes = [ip, dp, dp, ip, ip, ip, dp, dp, ip, dp, dp, dp, dp]
     lib.loglhood_batch_ar.restype = i

@@ -840,6 +840,28 @@ int dff_batch(const double *vels, const double *depths, const int *nlayers, cons
     return run_host(h);
 }
 
+void dff_batch_status(const double *vels, const double *depths, const int *nlayers, const int *B,
+                      const int *ldv, const int *ldz, const double *src_offset,
+                      const double *src_depth, const int *NSrc, double *timeP, const double *tobs,
+                      const double *sigma, double *logL, double *p_out, const int *want,
+                      int *status) {
+    const bool wt = want && want[0], wl = want && want[1], wp = want && want[2];
+    const int rc = dff_batch(vels, depths, nlayers, B, ldv, ldz, src_offset, src_depth, NSrc,
+                             wt ? timeP : nullptr, wl ? tobs : nullptr, wl ? sigma : nullptr,
+                             wl ? logL : nullptr, wp ? p_out : nullptr);
+    if (status) *status = rc;
+    if (rc != 0) complain();
+}
+
+void dff_batch_status_(const double *vels, const double *depths, const int *nlayers, const int *B,
+                       const int *ldv, const int *ldz, const double *src_offset,
+                       const double *src_depth, const int *NSrc, double *timeP, const double *tobs,
+                       const double *sigma, double *logL, double *p_out, const int *want,
+                       int *status) {
+    dff_batch_status(vels, depths, nlayers, B, ldv, ldz, src_offset, src_depth, NSrc, timeP, tobs,
+                     sigma, logL, p_out, want, status);
+}
+
 int loglhood_batch(const int *k, const double *vp, const double *ziface, const int *B,
                    const int *ldv, const int *ldz, const double *src_offset,
                    const double *src_depth, const int *NSrc, const double *tobs,

@@ -417,3 +417,33 @@ def test_one_model_latency_kernel_hostile_inputs():
             nan = np.isnan(w_)
             assert np.array_equal(np.isnan(g_), nan), (case, nm)
             assert np.array_equal(g_[~nan].view(np.uint64), w_[~nan].view(np.uint64)), (case, nm)
+
+
+def test_dff_batch_status_entry_for_r():
+    """dff_batch_status: every argument by pointer, status through an int* (R's .C / .Fortran
+    discard return values), optional outputs selected by the want flags."""
+    import ctypes as C
+    from raytracerfortran_b200 import _lib
+    lib = _lib.load()
+    B, nsrc = 300, 12
+    v, z, nl = workloads.make_models(B, 5, 3)
+    so, sd = workloads.make_sources(nsrc, 3)
+    tobs, sigma = workloads.make_observations(np.ones(nsrc), B, 3)
+    ref = rt.dff_batch(v, z, nl, so, sd, tobs=tobs, sigma=sigma, want_p=True)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    P = lambda a: a.ctypes.data_as(dp)
+    ci = lambda x: C.byref(C.c_int(x))
+    for name in ("dff_batch_status", "dff_batch_status_"):
+        t, ll, p = np.zeros((B, nsrc)), np.zeros(B), np.zeros(0)
+        want = np.array([1, 1, 0], dtype=np.int32)
+        status = C.c_int(-99)
+        getattr(lib, name)(P(v), P(z), nl.ctypes.data_as(ip), ci(B), ci(v.shape[1]), ci(z.shape[1]), P(so), P(sd),
+                           ci(nsrc), P(t), P(tobs), P(sigma), P(ll), P(p), want.ctypes.data_as(ip), C.byref(status))
+        assert status.value == 0
+        assert_bitexact(t, ref["timeP"], name)
+        assert np.array_equal(ll.view(np.uint64), ref["logL"].view(np.uint64))
+    # an impossible call reports through the status word instead of a return value
+    status = C.c_int(0)
+    lib.dff_batch_status(P(v), P(z), nl.ctypes.data_as(ip), ci(B), ci(0), ci(z.shape[1]), P(so), P(sd), ci(nsrc),
+                         P(t), P(tobs), P(sigma), P(ll), P(p), want.ctypes.data_as(ip), C.byref(status))
+    assert status.value != 0 and "ldv" in _lib.last_error()
