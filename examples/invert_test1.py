@@ -51,11 +51,15 @@ def main():
     tl = device.dff_batch_device(tv[:, 1, :].contiguous(), tv[:, 0, 1:].contiguous(), tk, ts, td,
                                  tobs=to, sigma=tg, kmode=True)["logL"]
     prior, sp, pk = chains.prior_array(), chains.sd_prior_array(), chains.poisson_pk(3.01, 1, NLMX)
-    gen = torch.Generator(device=dev).manual_seed(12)
+    # one CUDA graph per iteration (birth/death, 2*NLMX-1 moves of every chain's own sweep, sigma
+    # move; deviates drawn on the device), the swap round on a side stream in between
+    graph = chains.McmcGraph(tk, tv, tl, tg, tb, 2 * NLMX - 1, prior, sp, pk, 1, NLMX, ts, td, to, seed=12)
+    swap = tempering.SwapRound(B, dev)
     rows = []
     for it in range(args.iters):
-        chains.mcmc_step_device(tk, tv, tl, tg, tb, prior, sp, pk, 1, NLMX, ts, td, to, generator=gen)
-        tb, _ = tempering.tempering_swap_round_device(tl, tb, seed=12, round_index=it)
+        graph.run(1)
+        swap.launch(tl, tb, 12, it)                    # betas exchanged in place
+        swap.wait()
         if it >= args.iters // 2 and it % args.thin == 0:        # keep the T = 1 chains after burn-in
             cold = (tb == 1.0).nonzero().squeeze(1)
             rows.append(samplefile.pack_rows(tl[cold].cpu().numpy(), np.zeros(len(cold)), np.zeros(len(cold)),

@@ -70,6 +70,8 @@ def lib():
         _lib.orc_loglhood_voro.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, dp, C.c_double, dp, dp, dp]
         _lib.orc_loglhood_from_times_ar.restype = C.c_double
         _lib.orc_loglhood_from_times_ar.argtypes = [dp, dp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]
+        _lib.orc_set_ismpprior.restype = None
+        _lib.orc_set_ismpprior.argtypes = [C.c_int]
         _lib.orc_set_enos.restype = None
         _lib.orc_set_enos.argtypes = [C.c_int]
         _lib.orc_mh_step_batch.restype = None
@@ -298,3 +300,8 @@ def batch_stats(vels, depths, nlayers, src_offset, src_depth):
 def set_enos(enos):
     """ENOS switch of the move oracles (orc_set_enos): 1 = even-numbered order statistics prior."""
     lib().orc_set_enos(1 if enos else 0)
+
+
+def set_ismpprior(on):
+    """ISMPPRIOR switch of the move oracles (orc_set_ismpprior): 1 = LOGLHOOD2, logL = 1."""
+    lib().orc_set_ismpprior(1 if on else 0)

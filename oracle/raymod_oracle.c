@@ -515,10 +515,16 @@ void orc_set_chain_ar(const int *idxar, const double *arpar, double armx)
     g_ar_mx  = armx;
 }
 
+/* ISMPPRIOR = 1: the sampler draws from the prior, every likelihood is LOGLHOOD2's constant
+ * (loglhood.f90:704-716: obj%logL = 1). */
+static int g_ismpprior = 0;
+void orc_set_ismpprior(int on) { g_ismpprior = on ? 1 : 0; }
+
 static double chain_loglhood(int chain, int k, const double *vp, const double *ziface,
                              const double *src_offset, const double *src_depth, int nsrc,
                              const double *tobs, double sigma)
 {
+    if (g_ismpprior) return 1.0;
     if (!g_ar_idx || chain < 0)
         return orc_loglhood_rt(k, vp, ziface, src_offset, src_depth, nsrc, tobs, sigma, NULL);
     double *pred = (double *)malloc(sizeof(double) * (size_t)(nsrc > 0 ? nsrc : 1));

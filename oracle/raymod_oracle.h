@@ -111,6 +111,7 @@ void orc_set_chain_ar(const int *idxar, const double *arpar, double armx);
 /* "Next" rows N1 + N2: one fixed-dimension MH move of one chain -- PROPOSAL (ENOS = 0 Cauchy step,
  * prjmh_temper_rf.f90:1386-1447), INTERPLAYER_novar, CHECKBOUNDS2 (:1681-1716), LOGLHOOD and the
  * accept test of EXPLORE_MH_NOVARPAR (:739-757).  Random numbers are inputs.  See the .c file. */
+void orc_set_ismpprior(int on);   /* ISMPPRIOR = 1: every move's likelihood is LOGLHOOD2's constant 1 */
 void orc_set_enos(int enos);   /* ENOS = 1: order-statistics prior in the move oracles (default 0) */
 int orc_mh_step_chain(int chain, int k, double *node_depth, double *node_vp, double *logL,
                 int ivo, int iwhich, double cauchy, double u_acc, double beta, double sigma,

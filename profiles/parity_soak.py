@@ -20,7 +20,10 @@ t0 = time.time()
 rays = mism = batches = 0
 kinds = {}
 while time.time() - t0 < args.seconds:
-    kind = ["shallow", "deep-critical", "ragged", "kmode"][batches % 4]
+    kind = ["shallow", "deep-critical", "ragged", "kmode", "one-model"][batches % 5]
+    # round 2: every third batch through the opt-in queue kernel (variant 4; deep models fall back
+    # to their own kernel), and a kind of its own for the one-model latency kernel
+    rt.set_option("variant", 4 if batches % 3 == 2 else -1)
     seed = int(rng.integers(1, 2**31))
     if kind == "shallow":
         L, S, B = int(rng.integers(1, 13)), int(rng.integers(8, 129)), 60000
@@ -35,6 +38,23 @@ while time.time() - t0 < args.seconds:
         v, z, nl = workloads.make_models(B, L, seed)
         nl = rng.integers(0, L + 1, B).astype(np.int32)
         so, sd = workloads.make_sources(S, seed, near_critical=bool(seed & 1))
+    elif kind == "one-model":
+        rt.set_option("variant", -1)
+        bad = n = 0
+        for _ in range(200):
+            L, S = int(rng.integers(0, 60)), int(rng.integers(1, 400))
+            v, z, nl = workloads.make_models(1, max(L, 1), int(rng.integers(1, 2**31)), min_thickness=L < 40)
+            nl[:] = L
+            so, sd = workloads.make_sources(S, int(rng.integers(1, 2**31)), near_critical=bool(L & 1))
+            ref = oracle.dff_batch(v, z, nl, so, sd, want_p=True)
+            got = rt.dff_batch(v, z, nl, so, sd, want_p=True)
+            assert rt.get_stat("variant") == 5
+            bad += int((got["timeP"].view(np.uint64) != ref["timeP"].view(np.uint64)).sum()) \
+                + int((got["p"].view(np.uint64) != ref["p"].view(np.uint64)).sum())
+            n += S
+        rays += n; mism += bad; batches += 1
+        kinds[kind] = kinds.get(kind, 0) + n
+        continue
     else:
         S, B = int(rng.integers(16, 257)), 30000
         k, vp, zi = workloads.make_transd_models(B, 30, seed)
@@ -57,6 +77,7 @@ while time.time() - t0 < args.seconds:
     bad = int((got["timeP"].view(np.uint64) != ref["timeP"].view(np.uint64)).sum()) \
         + int((got["p"].view(np.uint64) != ref["p"].view(np.uint64)).sum())
     rays += B * S; mism += bad; batches += 1
-    kinds[kind] = kinds.get(kind, 0) + B * S
+    tag = kind + (" (variant 4)" if rt.get_stat("variant") == 4 else "")
+    kinds[tag] = kinds.get(tag, 0) + B * S
 print(json.dumps({"seconds": time.time() - t0, "batches": batches, "rays_compared": rays,
                   "bit_mismatches": mism, "rays_by_kind": kinds, "seed": args.seed}))

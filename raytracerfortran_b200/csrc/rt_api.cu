@@ -98,6 +98,7 @@ struct Ctx {
     size_t lat_cap = 0;
     int opt_latency = 1;           // 1: one-model calls take the latency kernel; 0: the batch kernel
     int opt_stable_lognorm = 0;    // 1: log-likelihood constant as -(N/2) log(2 pi) (finite for N >= 772)
+    int opt_ismpprior = 0;         // 1: the chain moves sample the prior (LOGLHOOD2: logL = 1)
     // options (<= 0: automatic)
     int opt_variant = -1, opt_threads = 0, opt_tile_models = 0, opt_tile_sources = 0,
         opt_chunk_models = 0, opt_ctas = 0, opt_logl_shuffle = 0, opt_comp_streams = 0, opt_static_tiles = 0;
@@ -419,12 +420,18 @@ void parallel_memcpy(void *dst, const void *src, size_t bytes) {
     }
     const size_t part = (bytes / nt + 63) & ~(size_t)63;
     std::vector<std::thread> th;
+    size_t done_to = std::min(part, bytes);       // [0, done_to) is this thread's; helpers take the rest
     for (size_t t = 1; t < nt; ++t) {
         const size_t o = t * part;
         if (o >= bytes) break;
-        th.emplace_back([=] { stream_copy((char *)dst + o, (const char *)src + o, std::min(part, bytes - o)); });
+        try {                                      // a host that cannot start another thread: copy it here
+            th.emplace_back([=] { stream_copy((char *)dst + o, (const char *)src + o, std::min(part, bytes - o)); });
+        } catch (...) {
+            stream_copy((char *)dst + o, (const char *)src + o, bytes - o);
+            break;
+        }
     }
-    stream_copy(dst, src, std::min(part, bytes));
+    stream_copy(dst, src, done_to);
     for (auto &t : th) t.join();
 }
 
@@ -1025,6 +1032,13 @@ BatchArgs move_eval_args(int B, int ldk, const double *d_src_offset, const doubl
     return a;
 }
 
+// The likelihood of a move's proposals: the batch kernel, or LOGLHOOD2's constant when the
+// sampler draws from the prior (ISMPPRIOR = 1, prjmh_temper_rf.f90:693-694, :739-740, ...).
+cudaError_t launch_move_eval(const BatchArgs &a, const TileCfg &cfg, cudaStream_t st) {
+    if (g.opt_ismpprior) return rtb::launch_fill_f64(a.logL, a.B, 1.0, st);
+    return rtb::launch_batch(a, cfg, st);
+}
+
 }  // namespace
 
 int rtb200_mh_step_device(const int *d_k, double *d_voro, double *d_logL, int B, int ldk,
@@ -1062,7 +1076,7 @@ int rtb200_mh_step_device_ev(const int *d_k, double *d_voro, double *d_logL, int
     const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, d_sigma,
                                        next_sched());
     CK(cudaEventRecord(g.ev_k0[0], st));
-    CK(rtb::launch_batch(a, cfg, st));
+    CK(launch_move_eval(a, cfg, st));
     CK(cudaEventRecord(g.ev_k1[0], st));
     // the proposal and its likelihood do not read beta; only the accept test does
     if (beta_ready_event) CK(cudaStreamWaitEvent(st, (cudaEvent_t)beta_ready_event, 0));
@@ -1121,7 +1135,7 @@ int rtb200_mh_moves_device_ex(const int *d_k, double *d_voro, double *d_logL, in
                                (size_t)g.vsorted.p, (size_t)g.mh_ll.p, (size_t)g.mh_out.p,
                                (size_t)cfg.M, (size_t)cfg.grid, (size_t)cfg.variant, (size_t)g.opt_static_tiles,
                                (size_t)g.chain_idxar, (size_t)g.chain_arpar, (size_t)(enos ? 1 : 0),
-                               (size_t)g.mh_lpr.p};
+                               (size_t)g.mh_lpr.p, (size_t)g.opt_ismpprior};
     {
         size_t bits;
         memcpy(&bits, &g.chain_armx, sizeof bits);
@@ -1147,7 +1161,7 @@ int rtb200_mh_moves_device_ex(const int *d_k, double *d_voro, double *d_logL, in
             if (e != cudaSuccess) break;
             const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, d_sigma,
                                                g.opt_static_tiles ? nullptr : g.sched.as<int>() + 2 * (kSchedSlots + m));
-            e = rtb::launch_batch(a, cfg, g.s_cap);
+            e = launch_move_eval(a, cfg, g.s_cap);
             if (e != cudaSuccess) break;
             e = rtb::launch_mh_accept(d_k, d_voro, g.vsorted.as<double>(), d_logL, g.mh_ll.as<double>(),
                                       g.mh_lpr.as<double>(), g.mh_out.as<int>(), d_uacc + o, d_beta, B, ldk,
@@ -1210,7 +1224,7 @@ int rtb200_bd_step_device_ex(int *d_k, double *d_voro, double *d_logL, int B, in
     const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, d_sigma,
                                        next_sched());
     CK(cudaEventRecord(g.ev_k0[0], st));
-    CK(rtb::launch_batch(a, cfg, st));
+    CK(launch_move_eval(a, cfg, st));
     CK(cudaEventRecord(g.ev_k1[0], st));
     CK(rtb::launch_bd_accept(d_k, d_voro, g.vsorted.as<double>(), g.mh_kp.as<int>(),
                              g.mh_lpr.as<double>(), d_logL, g.mh_ll.as<double>(),
@@ -1249,7 +1263,7 @@ int rtb200_sd_step_device(const int *d_k, const double *d_voro, double *d_logL, 
     const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, g.mh_lpr.as<double>(),
                                        next_sched());
     CK(cudaEventRecord(g.ev_k0[0], st));
-    CK(rtb::launch_batch(a, cfg, st));
+    CK(launch_move_eval(a, cfg, st));
     CK(cudaEventRecord(g.ev_k1[0], st));
     CK(rtb::launch_sd_accept(d_sigma, g.mh_lpr.as<double>(), d_logL, g.mh_ll.as<double>(),
                              g.mh_out.as<int>(), d_uacc, d_beta, B, d_accept, st));
@@ -1303,7 +1317,7 @@ int rtb200_ar_step_device(const int *d_k, const double *d_voro, double *d_logL,
     a.arpar = g.arparb.as<double>();
     a.armx  = ar_prior[3];
     CK(cudaEventRecord(g.ev_k0[0], st));
-    CK(rtb::launch_batch(a, cfg, st));
+    CK(launch_move_eval(a, cfg, st));
     CK(cudaEventRecord(g.ev_k1[0], st));
     CK(rtb::launch_ar_accept(d_idxar, d_arpar, g.idxar.as<int>(), g.arparb.as<double>(),
                              g.mh_lpr.as<double>(), d_logL, g.mh_ll.as<double>(), g.mh_out.as<int>(),
@@ -1358,7 +1372,7 @@ int rtb200_mcmc_iterations_device(int *d_k, double *d_voro, double *d_logL, doub
                                (size_t)g.vels.p, (size_t)g.depths.p, (size_t)g.nl.p, (size_t)g.vsorted.p,
                                (size_t)g.mh_ll.p, (size_t)g.mh_out.p, (size_t)g.mh_kp.p, (size_t)g.mh_lpr.p,
                                (size_t)cfg.M, (size_t)cfg.grid, (size_t)cfg.variant, (size_t)g.opt_static_tiles,
-                               (size_t)g.chain_idxar, (size_t)g.chain_arpar, (size_t)(pk ? 1 : 0)};
+                               (size_t)g.chain_idxar, (size_t)g.chain_arpar, (size_t)(pk ? 1 : 0), (size_t)g.opt_ismpprior};
     auto push_bits = [&](double x) { size_t bits; memcpy(&bits, &x, sizeof bits); key.push_back(bits); };
     push_bits(g.chain_armx);
     for (int i = 0; i < 7; ++i) push_bits(prior[i]);
@@ -1386,7 +1400,7 @@ int rtb200_mcmc_iterations_device(int *d_k, double *d_voro, double *d_logL, doub
                                       g.mh_kp.as<int>(), g.vsorted.as<double>(), g.mh_lpr.as<double>(),
                                       g.mh_out.as<int>(), sc));
             const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, d_sigma, slot(0));
-            if (e == cudaSuccess) ok(rtb::launch_batch(a, cfg, sc));
+            if (e == cudaSuccess) ok(launch_move_eval(a, cfg, sc));
             if (e == cudaSuccess)
                 ok(rtb::launch_bd_accept(d_k, d_voro, g.vsorted.as<double>(), g.mh_kp.as<int>(),
                                          g.mh_lpr.as<double>(), d_logL, g.mh_ll.as<double>(),
@@ -1401,7 +1415,7 @@ int rtb200_mcmc_iterations_device(int *d_k, double *d_voro, double *d_logL, doub
                                         g.vels.as<double>(), g.depths.as<double>(), g.nl.as<int>(),
                                         g.vsorted.as<double>(), g.mh_lpr.as<double>(), g.mh_out.as<int>(), sc));
             const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, d_sigma, slot(1 + m));
-            if (e == cudaSuccess) ok(rtb::launch_batch(a, cfg, sc));
+            if (e == cudaSuccess) ok(launch_move_eval(a, cfg, sc));
             if (e == cudaSuccess)
                 ok(rtb::launch_mh_accept(d_k, d_voro, g.vsorted.as<double>(), d_logL, g.mh_ll.as<double>(),
                                          g.mh_lpr.as<double>(), g.mh_out.as<int>(), w.u_acc + o, d_beta, B, ldk,
@@ -1414,7 +1428,7 @@ int rtb200_mcmc_iterations_device(int *d_k, double *d_voro, double *d_logL, doub
                                       g.mh_lpr.as<double>(), g.mh_out.as<int>(), sc));
             const BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc,
                                                g.mh_lpr.as<double>(), slot(1 + n_moves));
-            if (e == cudaSuccess) ok(rtb::launch_batch(a, cfg, sc));
+            if (e == cudaSuccess) ok(launch_move_eval(a, cfg, sc));
             if (e == cudaSuccess)
                 ok(rtb::launch_sd_accept(d_sigma, g.mh_lpr.as<double>(), d_logL, g.mh_ll.as<double>(),
                                          g.mh_out.as<int>(), w.u_acc_sd, d_beta, B, w.acc_sd, sc));
@@ -1538,6 +1552,7 @@ int rtb200_set_option(const char *name, double value) {
     else if (!strcmp(name, "stage_pageable")) g.opt_stage = v < 0 ? -1 : (v > 0 ? 1 : 0);
     else if (!strcmp(name, "latency_path")) g.opt_latency = v == 0 ? 0 : 1;
     else if (!strcmp(name, "stable_lognorm")) g.opt_stable_lognorm = v > 0 ? 1 : 0;
+    else if (!strcmp(name, "ismpprior")) g.opt_ismpprior = v > 0 ? 1 : 0;
     else return -1;
     return 0;
 }

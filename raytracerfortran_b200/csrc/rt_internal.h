@@ -45,7 +45,7 @@ struct BatchArgs {
 // Variant 4's shared-memory geometry, precomputed by the host (launch_batch) so that the kernel
 // reads every offset as a constant-bank operand: byte offsets from the dynamic smem base.
 struct QGeom {
-    uint32_t tab, src, T, q, st, ctr;    // tables, sources, travel-time slots, ray queues, ray state, counters
+    uint32_t tab, src, T, q, st, ctr, nlm;   // tables, sources, travel-time slots, ray queues / list, ray state, counters, model flags
     uint32_t rowB, lp8;                  // bytes per model row of the tables, per sub-table
     uint32_t oHV, oZ, oVV, oIVM;         // sub-table offsets inside a model row
     uint32_t oD;                         // source depths after the offsets
@@ -151,6 +151,7 @@ cudaError_t launch_ar_accept(int *idxar, double *arpar, const int *idx_prop, con
                              int *accept, cudaStream_t st);
 cudaError_t launch_dff_latency(const double *in_host, const double *in_dev, int NL, int S, double *out,
                                int want_p, int *done_flag, int *single_cta, cudaStream_t st);
+cudaError_t launch_fill_f64(double *p, int n, double value, cudaStream_t st);
 cudaError_t launch_swap_pack(const double *logL, const double *beta, int n, double *out,
                              cudaStream_t st);
 cudaError_t launch_swap_round(const double *all, int n, int lo, int n_local, unsigned long long seed,

@@ -286,3 +286,26 @@ def test_enos_rules(cfg1):
                     assert bd(0.2, u_z=u_z, u_v=0.25, u_acc=uu)["accept"][0] == (0 if uu >= thr else 1)
     finally:
         oracle.set_enos(0)
+
+
+def test_mcmc_workspace_layout():
+    """chains.mcmc_workspace_views mirrors the C layout (McmcWs, csrc/rt_internal.h): the views
+    tile the workspace exactly, in the documented order, and the size is what the library reports
+    (rtb200_mcmc_workspace_bytes is plain arithmetic: no GPU needed)."""
+    import torch
+    from raytracerfortran_b200 import _lib
+    for B, M in ((1, 0), (7, 3), (100, 19)):
+        n = _lib.load().rtb200_mcmc_workspace_bytes(B, M)
+        assert n == (7 + 2 * M) * B * 8 + (3 + 3 * M) * B * 4
+        ws = torch.zeros(n, dtype=torch.uint8)
+        v = chains.mcmc_workspace_views(ws, B, M)
+        order = ["u_k", "u_z", "u_v", "u_acc_bd", "u_gate", "gauss", "u_acc_sd", "dev", "u_acc",
+                 "idel", "acc_bd", "acc_sd", "ivo", "iwhich", "acc_mh"]
+        off = 0
+        for name in order:
+            t = v[name]
+            assert t.numel() == 0 or t.data_ptr() - ws.data_ptr() == off, name
+            off += t.numel() * t.element_size()
+            assert t.shape == ((M, B) if name in ("dev", "u_acc", "ivo", "iwhich", "acc_mh") else (B,))
+        assert off == n
+    assert _lib.load().rtb200_mcmc_workspace_bytes(0, 5) == 0

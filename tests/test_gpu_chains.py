@@ -595,3 +595,56 @@ def test_mcmc_graph_iteration_matches_oracle(enos):
     assert int(g.counter.item()) == 23
     kk = tk.cpu().numpy()
     assert kk.min() >= kmin and kk.max() <= kmax and np.isfinite(tl.cpu().numpy()).all()
+
+
+def test_prior_sampling_mode_matches_oracle():
+    """ISMPPRIOR = 1: every proposal's likelihood is LOGLHOOD2's constant (loglhood.f90:704-716), so
+    inside-the-bounds proposals are accepted by the prior ratio alone; same decisions and states as
+    the oracle, through the single moves and the whole-iteration graph."""
+    import torch
+    import raytracerfortran_b200 as rt
+    B, ldk, nsrc, M = 1200, 10, 16, 5
+    k, voro, so, sd, tobs, sigma, _ = _setup(B, ldk, nsrc, 101)
+    ll = np.ones(B)                                     # LOGLHOOD2 of the starting states (:256-257)
+    rng = np.random.default_rng(102)
+    prior, sd_prior, pk = chains.prior_array(), chains.sd_prior_array(), chains.poisson_pk(3.01, 1, ldk)
+    beta = 1.0 / 1.4 ** rng.integers(0, 6, B)
+    tk, tv, tl, tg, tb, ts, td, to = _dev(k, voro, ll, sigma, beta, so, sd, tobs)
+    rt.set_option("ismpprior", 1)
+    oracle.set_ismpprior(1)
+    try:
+        ivo = np.minimum(2, k).astype(np.int32)
+        iwhich = rng.integers(1, 3, B).astype(np.int32)
+        u = rng.random((2, B))
+        cauchy = 0.3 * np.tan(np.pi * (u[0] - 0.5))
+        r = oracle.mh_step_batch(k, voro, ll, ivo, iwhich, cauchy, u[1], beta, sigma, prior, so, sd, tobs)
+        ti, tw, tc, tu = _dev(ivo, iwhich, cauchy, u[1])
+        acc = chains.mh_step_device(tk, tv, tl, ti, tw, tc, tu, tb, tg, prior, ts, td, to).cpu().numpy()
+        assert np.array_equal(acc, r["accept"]) and set(np.unique(acc)) <= {1, -1}      # never rejected inside
+        assert np.array_equal(tv.cpu().numpy().view(np.uint64), r["voro"].view(np.uint64))
+        assert np.all(tl.cpu().numpy() == 1.0)
+        cur_k, cur_v, cur_l, cur_s = k.copy(), r["voro"], r["logL"], sigma.copy()
+        g = chains.McmcGraph(tk, tv, tl, tg, tb, M, prior, sd_prior, pk, 1, ldk, ts, td, to, seed=9)
+        pos = np.zeros(B, dtype=np.int64)
+        for it in range(2):
+            g.run(1)
+            torch.cuda.synchronize()
+            w = {n: t.cpu().numpy().copy() for n, t in g.views.items()}
+            rr = oracle.bd_step_batch(cur_k, cur_v, cur_l, w["u_k"], w["idel"], w["u_z"], w["u_v"], w["u_acc_bd"],
+                                      beta, cur_s, prior, pk, 1, ldk, so, sd, tobs)
+            assert np.array_equal(w["acc_bd"], rr["accept"])
+            cur_k, cur_v, cur_l = rr["k"], rr["voro"], rr["logL"]
+            for m in range(M):
+                rr = oracle.mh_step_batch(cur_k, cur_v, cur_l, w["ivo"][m], w["iwhich"][m], w["dev"][m], w["u_acc"][m],
+                                          beta, cur_s, prior, so, sd, tobs)
+                assert np.array_equal(w["acc_mh"][m], rr["accept"])
+                cur_v, cur_l = rr["voro"], rr["logL"]
+            rr = oracle.sd_step_batch(cur_k, cur_v, cur_l, cur_s, w["u_gate"], w["gauss"], w["u_acc_sd"], beta,
+                                      sd_prior, so, sd, tobs)
+            assert np.array_equal(w["acc_sd"], rr["accept"])
+            cur_l, cur_s = rr["logL"], rr["sigma"]
+            assert np.array_equal(tv.cpu().numpy().view(np.uint64), cur_v.view(np.uint64))
+            assert np.array_equal(tg.cpu().numpy().view(np.uint64), cur_s.view(np.uint64))
+    finally:
+        rt.set_option("ismpprior", 0)
+        oracle.set_ismpprior(0)

@@ -70,3 +70,53 @@ def test_swap_round_overlaps_with_other_work():
     torch.cuda.synchronize()
     assert np.array_equal(got.cpu().numpy().view(np.uint64), ref.view(np.uint64))
     assert busy.numel() == 1 << 20
+
+
+def test_overlapped_swap_rounds_equal_the_sequential_schedule():
+    """The bench's config-4 step: MH move of every chain, then a swap round launched on a side
+    stream under the NEXT step's proposal and likelihood kernels (only the accept test waits for the
+    new betas).  The chain states after ten such steps equal, bit for bit, those of the same steps
+    run one after the other with a synchronise in between."""
+    from raytracerfortran_b200 import chains, device, workloads
+    dev = torch.device("cuda", 0)
+    B, ldk, nsrc, steps = 4096, 12, 32, 10
+    k, vp, zi = workloads.make_transd_models(B, ldk, 77)
+    voro = np.zeros((B, 2, ldk))
+    voro[:, 1, :] = vp
+    voro[:, 0, 1:] = zi
+    so, sd = workloads.make_sources(nsrc, 77)
+    tobs, sigma = workloads.make_observations(np.full(nsrc, 1.3), B, 77)
+    f = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    ts, td, to, tg = f(so), f(sd), f(tobs), f(sigma)
+    prior = chains.prior_array()
+    gen = torch.Generator(device=dev).manual_seed(3)
+    tk0 = f(k)
+    period = (2 * tk0 - 1).to(torch.int64)
+    j = torch.arange(steps, device=dev, dtype=torch.int64)[:, None] % period[None, :] + 1
+    ivo = (torch.div(j, 2, rounding_mode="floor") + 1).to(torch.int32).contiguous()
+    iwh = (j % 2 + 1).to(torch.int32).contiguous()
+    u = torch.rand((2, steps, B), dtype=torch.float64, device=dev, generator=gen)
+    cauchy, uacc = (0.2 * chains.cauchy_deviates(u[0])).contiguous(), u[1].contiguous()
+    ladder = np.repeat(tempering.temperature_ladder(64, 1.3), B // 64)
+
+    def run(overlap):
+        tv, beta = f(voro), f(ladder)
+        tl = device.dff_batch_device(tv[:, 1, :].contiguous(), tv[:, 0, 1:].contiguous(), tk0, ts, td,
+                                     tobs=to, sigma=tg, kmode=True)["logL"]
+        sr = tempering.SwapRound(B, dev)
+        acc = torch.empty(B, dtype=torch.int32, device=dev)
+        for i in range(steps):
+            chains.mh_step_device(tk0, tv, tl, ivo[i], iwh[i], cauchy[i], uacc[i], beta, tg, prior, ts, td, to,
+                                  accept=acc, beta_ready=sr.done if (overlap and i > 0) else None)
+            sr.launch(tl, beta, 11, i)
+            if not overlap:
+                sr.wait()
+                torch.cuda.synchronize()
+        sr.wait()
+        torch.cuda.synchronize()
+        return tv.cpu().numpy(), tl.cpu().numpy(), beta.cpu().numpy()
+
+    a, b = run(False), run(True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x.view(np.uint64), y.view(np.uint64))
+    assert not np.array_equal(a[2], ladder)              # swaps did happen
