@@ -334,7 +334,8 @@ int         rtb200_init(int device);          /* optional; lazy init picks the d
 void        rtb200_shutdown(void);
 const char *rtb200_last_error(void);          /* "" when the last call succeeded               */
 int         rtb200_device_count(void);        /* 0 without a driver / device                   */
-/* options: "variant" (0 plain loops, 1 lane state machine, 3 deep-model kernel, < 0 by depth),
+/* options: "variant" (0 plain loops, 1 lane state machine, 3 deep-model kernel, 4 ray-queue kernel
+ *          (experimental, up to 62 velocities per model), < 0 default: 1, or 3 for deep models),
  *          "threads", "tile_models", "tile_sources", "chunk_models", "ctas_per_sm"; <= 0 restores
  *          the default; "comp_streams" (1: host-call chunks run on one compute stream; default 2:
  *          consecutive chunks alternate between two so one chunk's tail overlaps the next);

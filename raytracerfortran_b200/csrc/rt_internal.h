@@ -54,13 +54,14 @@ struct QGeom {
 
 // Tile geometry chosen by the host for one launch.
 struct TileCfg {
-    int M;        // models per tile (even)
+    int M;        // models per tile (even unless forced by the tile_models option)
     int SC;       // sources per chunk
     int LP;       // per-model row length of the derived tables (odd, >= max velocities)
     int TS;       // row stride of the travel-time tile (odd)
     int threads;  // CTA size
     int grid;     // persistent CTAs
-    int variant;  // 0: plain per-thread loops, 1: lane state machine with refill, 3: the same for deep models
+    int variant;  // 0: plain per-thread loops, 1: lane state machine with refill, 3: the same for deep models,
+                  // 4: level-synchronous ray queues (opt-in)
     int use_tma;  // rows are 16-byte aligned: stage with cp.async.bulk
     int logl_shuffle;  // reduce the residuals with warp shuffles (tree order) instead of source order
     size_t smem;  // dynamic shared memory bytes
