@@ -486,7 +486,12 @@ def main():
     count_w = world == 1 and not args.no_cpu
     configs = None
     if not args.models:
-        configs = other_configs(torch, dist, rt, rank, world, dev, peak_tf, count_w and rank == 0)
+        try:
+            configs = other_configs(torch, dist, rt, rank, world, dev, peak_tf, count_w and rank == 0)
+        except Exception as e:       # the headline line must survive a failure in the extra shapes
+            import traceback
+            traceback.print_exc()
+            configs = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         evals_step = float(B) * S * world
