@@ -45,7 +45,7 @@ struct BatchArgs {
 // Variant 4's shared-memory geometry, precomputed by the host (launch_batch) so that the kernel
 // reads every offset as a constant-bank operand: byte offsets from the dynamic smem base.
 struct QGeom {
-    uint32_t tab, src, T, q, st, ctr, nlm;   // tables, sources, travel-time slots, ray queues / list, ray state, counters, model flags
+    uint32_t tab, src, T, q, st, ctr;    // tables, sources, travel-time slots, ray queues, ray state, counters
     uint32_t rowB, lp8;                  // bytes per model row of the tables, per sub-table
     uint32_t oHV, oZ, oVV, oIVM;         // sub-table offsets inside a model row
     uint32_t oD;                         // source depths after the offsets
