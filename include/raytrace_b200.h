@@ -289,15 +289,18 @@ int rtb200_ar_step_device(const int *d_k, const double *d_voro, double *d_logL,
  * EXPLORE_MH (:545-575).  Every random deviate is drawn by the library's Philox4x32-10 kernels
  * (key = seed, counter = (chain, *d_counter, purpose)); the iteration is captured once as a CUDA
  * graph and replayed, *d_counter advancing by one per iteration, so there is no host
- * synchronisation and no per-move host work.  The chains' AR(1) state, if registered
- * (rtb200_set_chain_ar), enters every likelihood; the AR move itself is not part of the graph.
+ * synchronisation and no per-move host work.  With d_idxar / d_arpar / ar_prior (IAR = 1; all
+ * three or none) the iteration ends with EXPLORE_MH's AR(1) move (:583-631) and every likelihood
+ * of the iteration uses the chains' AR state; without them a state registered through
+ * rtb200_set_chain_ar still enters every likelihood.
  *   d_k, d_voro, d_logL, d_sigma in/out; d_beta [B] read at every accept test (a swap round
  *   between calls may rewrite it); d_pos [B] i32 in/out: position of each chain in its sweep
  *   prior HOST [7], sd_prior HOST [3], pk HOST [kmax] or NULL, enos: as for the single moves
  *   d_counter: one device uint64, in/out;  d_workspace: rtb200_mcmc_workspace_bytes(B, n_moves)
  *   bytes holding the iteration's deviates and outcomes (layout: McmcWs in csrc/rt_internal.h,
- *   mirrored by chains.mcmc_workspace_views);  d_tally [4][B] int64 or NULL, accumulated:
- *   fixed-dimension moves accepted, evaluated, births/deaths accepted, sigma moves accepted */
+ *   mirrored by chains.mcmc_workspace_views);  d_tally [5][B] int64 or NULL, accumulated:
+ *   fixed-dimension moves accepted, evaluated, births/deaths accepted, sigma moves accepted,
+ *   AR moves accepted;  ar_prior HOST [4] as for rtb200_ar_step_device */
 size_t rtb200_mcmc_workspace_bytes(int B, int n_moves);
 int rtb200_mcmc_iterations_device(int *d_k, double *d_voro, double *d_logL, double *d_sigma,
                                   const double *d_beta, int *d_pos, int B, int ldk, int n_moves,
@@ -306,6 +309,7 @@ int rtb200_mcmc_iterations_device(int *d_k, double *d_voro, double *d_logL, doub
                                   const double *d_src_depth, const double *d_tobs, int NSrc,
                                   unsigned long long seed, unsigned long long *d_counter,
                                   void *d_workspace, long long *d_tally, int n_iterations,
+                                  int *d_idxar, double *d_arpar, const double *ar_prior,
                                   void *stream);
 
 /* The parallel-tempering swap round (TEMPSWP_MH, prjmh_temper_rf.f90:1329-1384; master loop

@@ -85,7 +85,7 @@ def load():
     lib.rtb200_mcmc_workspace_bytes.argtypes = [i, i]
     lib.rtb200_mcmc_iterations_device.restype = i
     lib.rtb200_mcmc_iterations_device.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, dp, dp, dp, i, i, i, vp, vp, vp, i,
-                                                  C.c_ulonglong, vp, vp, vp, i, vp]
+                                                  C.c_ulonglong, vp, vp, vp, i, vp, vp, dp, vp]
     lib.rtb200_swap_pack_device.restype = i
     lib.rtb200_swap_pack_device.argtypes = [vp, vp, i, vp, vp]
     lib.rtb200_swap_round_device.restype = i

@@ -342,32 +342,34 @@ def _mcmc_step(k, voro, logL, sigma, beta, prior, sd_prior, pk, kmin, kmax, src_
 def mcmc_workspace_views(workspace, B, n_moves):
     """Named views into the workspace of rtb200_mcmc_iterations_device (a uint8 CUDA tensor of
     rtb200_mcmc_workspace_bytes(B, n_moves) bytes; layout: McmcWs, csrc/rt_internal.h): the
-    iteration's deviates (u_k, u_z, u_v, u_acc_bd, u_gate, gauss, u_acc_sd [B]; dev, u_acc
-    [M, B]; idel [B]; ivo, iwhich [M, B]) and outcomes (acc_bd, acc_sd [B]; acc_mh [M, B])."""
+    iteration's deviates (u_k, u_z, u_v, u_acc_bd, u_gate, gauss, u_acc_sd, u_choice, u_prop_ar,
+    gauss_ar, u_acc_ar [B]; dev, u_acc [M, B]; idel [B]; ivo, iwhich [M, B]) and outcomes (acc_bd,
+    acc_sd, acc_ar [B]; acc_mh [M, B])."""
     M = int(n_moves)
-    nd = (7 + 2 * M) * B
+    nd = (11 + 2 * M) * B
     d = workspace[:nd * 8].view(torch.float64)
-    i = workspace[nd * 8:nd * 8 + (3 + 3 * M) * B * 4].view(torch.int32)
-    names_d = ["u_k", "u_z", "u_v", "u_acc_bd", "u_gate", "gauss", "u_acc_sd"]
+    i = workspace[nd * 8:nd * 8 + (4 + 3 * M) * B * 4].view(torch.int32)
+    names_d = ["u_k", "u_z", "u_v", "u_acc_bd", "u_gate", "gauss", "u_acc_sd", "u_choice", "u_prop_ar",
+               "gauss_ar", "u_acc_ar"]
     out = {n: d[j * B:(j + 1) * B] for j, n in enumerate(names_d)}
-    out["dev"] = d[7 * B:(7 + M) * B].view(M, B)
-    out["u_acc"] = d[(7 + M) * B:(7 + 2 * M) * B].view(M, B)
-    out["idel"], out["acc_bd"], out["acc_sd"] = i[:B], i[B:2 * B], i[2 * B:3 * B]
-    out["ivo"] = i[3 * B:(3 + M) * B].view(M, B)
-    out["iwhich"] = i[(3 + M) * B:(3 + 2 * M) * B].view(M, B)
-    out["acc_mh"] = i[(3 + 2 * M) * B:(3 + 3 * M) * B].view(M, B)
+    out["dev"] = d[11 * B:(11 + M) * B].view(M, B)
+    out["u_acc"] = d[(11 + M) * B:(11 + 2 * M) * B].view(M, B)
+    out["idel"], out["acc_bd"], out["acc_sd"], out["acc_ar"] = i[:B], i[B:2 * B], i[2 * B:3 * B], i[3 * B:4 * B]
+    out["ivo"] = i[4 * B:(4 + M) * B].view(M, B)
+    out["iwhich"] = i[(4 + M) * B:(4 + 2 * M) * B].view(M, B)
+    out["acc_mh"] = i[(4 + 2 * M) * B:(4 + 3 * M) * B].view(M, B)
     return out
 
 
 class McmcGraph:
     """The sampler's worker loop (prjmh_temper_rf.f90:420-458) for B chains as one CUDA graph per
     iteration, random numbers included (rtb200_mcmc_iterations_device): birth/death move, `n_moves`
-    fixed-dimension moves of every chain's own sweep, data-error move.  Owns the sweep positions,
+    fixed-dimension moves of every chain's own sweep, data-error move, and with `ar` the AR(1) move.  Owns the sweep positions,
     the device iteration counter, the workspace and the tallies; `run(n)` replays the graph n
     times without touching the host again."""
 
     def __init__(self, k, voro, logL, sigma, beta, n_moves, prior, sd_prior, pk, kmin, kmax,
-                 src_offset, src_depth, tobs, seed=1, enos=False, counter0=0):
+                 src_offset, src_depth, tobs, seed=1, enos=False, counter0=0, ar=None):
         dev = voro.device
         _ensure_device(dev.index if dev.index is not None else torch.cuda.current_device())
         self.k, self.voro, self.logL, self.sigma, self.beta = k, voro, logL, sigma, beta
@@ -386,7 +388,15 @@ class McmcGraph:
         self.counter = torch.tensor([int(counter0)], dtype=torch.int64, device=dev)
         nbytes = _lib.load().rtb200_mcmc_workspace_bytes(self.B, self.M)
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-        self.tally = torch.zeros((4, self.B), dtype=torch.int64, device=dev)
+        self.tally = torch.zeros((5, self.B), dtype=torch.int64, device=dev)
+        # IAR = 1: ar = (idxar [B] i32, arpar [B] f64, ar_prior (ar_prior_array)); the iteration then
+        # ends with the AR(1) move and every likelihood uses the chains' AR state
+        self.ar = None
+        if ar is not None:
+            ap = np.ascontiguousarray(ar[2], dtype=np.float64)
+            if ap.size != 4:
+                raise ValueError("ar_prior must hold 4 doubles (see ar_prior_array)")
+            self.ar = (ar[0], ar[1], ap)
         self.views = mcmc_workspace_views(self.workspace, self.B, self.M)
 
     def run(self, n_iterations=1, stream=None):
@@ -402,5 +412,8 @@ class McmcGraph:
             1 if self.enos else 0, _ptr(so, f64), _ptr(sd, f64), _ptr(ob, f64), so.numel(),
             self.seed & 0xFFFFFFFFFFFFFFFF, self.counter.data_ptr(), self.workspace.data_ptr(),
             self.tally.data_ptr(), int(n_iterations),
+            None if self.ar is None else _ptr(self.ar[0], i32),
+            None if self.ar is None else _ptr(self.ar[1], f64),
+            None if self.ar is None else self.ar[2].ctypes.data_as(dp),
             st.cuda_stream if st.cuda_stream != 0 else _legacy_stream_handle())
         _lib.check(rc)

@@ -1349,15 +1349,18 @@ int rtb200_mcmc_iterations_device(int *d_k, double *d_voro, double *d_logL, doub
                                   const double *d_src_depth, const double *d_tobs, int NSrc,
                                   unsigned long long seed, unsigned long long *d_counter,
                                   void *d_workspace, long long *d_tally, int n_iterations,
+                                  int *d_idxar, double *d_arpar, const double *ar_prior,
                                   void *stream) {
     if (int rc = ensure_init()) return rc;
     g.err.clear();
     if (B <= 0 || n_iterations <= 0) return 0;
+    if ((d_idxar == nullptr) != (d_arpar == nullptr) || (d_idxar && !ar_prior))
+        return fail("rtb200_mcmc_iterations_device: the AR move needs idxar, arpar and ar_prior together");
     if (NSrc <= 0) return fail("rtb200_mcmc_iterations_device needs at least one source");
     if (ldk < 1 || ldk > 64) return fail("rtb200_mcmc_iterations_device supports 1..64 nodes per state");
     if (!prior || !sd_prior) return fail("rtb200_mcmc_iterations_device needs the prior and sd_prior arrays");
     if (kmin < 1 || kmax < kmin || kmax > ldk) return fail("rtb200_mcmc_iterations_device needs 1 <= kmin <= kmax <= ldk");
-    if (n_moves < 0 || n_moves + 2 > kGraphSlots) return fail("rtb200_mcmc_iterations_device: at most 510 moves per iteration");
+    if (n_moves < 0 || n_moves + 3 > kGraphSlots) return fail("rtb200_mcmc_iterations_device: at most 509 moves per iteration");
     if (!d_counter || !d_workspace || !d_pos) return fail("rtb200_mcmc_iterations_device needs counter, workspace and pos");
     cudaStream_t st = stream ? (cudaStream_t)stream : g.s_comp;
     TileCfg cfg;
@@ -1365,6 +1368,19 @@ int rtb200_mcmc_iterations_device(int *d_k, double *d_voro, double *d_logL, doub
     if (int rc = reserve_move_scratch(B, ldk, cfg)) return rc;
     if (int rc = scratch_acquire(st)) return rc;
     const rtb::McmcWs w = rtb::mcmc_ws_layout(d_workspace, (size_t)B, (size_t)n_moves);
+    // IAR = 1: with the AR move in the iteration, every likelihood of the iteration uses the chains'
+    // AR state (as if registered with rtb200_set_chain_ar); the registration is restored on return
+    struct ArScope {
+        const int *i; const double *a; double m; bool on;
+        ~ArScope() { if (on) { g.chain_idxar = i; g.chain_arpar = a; g.chain_armx = m; } }
+    } ar_scope{g.chain_idxar, g.chain_arpar, g.chain_armx, d_idxar != nullptr};
+    if (d_idxar) {
+        g.chain_idxar = d_idxar;
+        g.chain_arpar = d_arpar;
+        g.chain_armx  = ar_prior[3];
+        CK(g.idxar.reserve((size_t)B * 4));
+        CK(g.arparb.reserve((size_t)B * 8));
+    }
     std::vector<size_t> key = {(size_t)d_k, (size_t)d_voro, (size_t)d_logL, (size_t)d_sigma, (size_t)d_beta,
                                (size_t)d_pos, (size_t)B, (size_t)ldk, (size_t)n_moves, (size_t)kmin, (size_t)kmax,
                                (size_t)(enos ? 1 : 0), (size_t)d_src_offset, (size_t)d_src_depth, (size_t)d_tobs,
@@ -1378,6 +1394,11 @@ int rtb200_mcmc_iterations_device(int *d_k, double *d_voro, double *d_logL, doub
     for (int i = 0; i < 7; ++i) push_bits(prior[i]);
     for (int i = 0; i < 3; ++i) push_bits(sd_prior[i]);
     for (int i = kmin; pk && i <= kmax; ++i) push_bits(pk[i - 1]);
+    key.push_back((size_t)d_idxar);
+    key.push_back((size_t)d_arpar);
+    key.push_back((size_t)g.idxar.p);
+    key.push_back((size_t)g.arparb.p);
+    for (int i = 0; d_idxar && i < 4; ++i) push_bits(ar_prior[i]);
     if (!g.mc_exec || key != g.mc_key) {
         if (g.mc_exec) { cudaGraphExecDestroy(g.mc_exec); g.mc_exec = nullptr; }
         if (!g.s_cap) CK(cudaStreamCreateWithFlags(&g.s_cap, cudaStreamNonBlocking));
@@ -1433,6 +1454,23 @@ int rtb200_mcmc_iterations_device(int *d_k, double *d_voro, double *d_logL, doub
                 ok(rtb::launch_sd_accept(d_sigma, g.mh_lpr.as<double>(), d_logL, g.mh_ll.as<double>(),
                                          g.mh_out.as<int>(), w.u_acc_sd, d_beta, B, w.acc_sd, sc));
         }
+        // ---- the AR(1) move (IAR = 1)
+        if (e == cudaSuccess && d_idxar) {
+            ok(rtb::launch_propose_ar(d_k, d_voro, B, ldk, d_idxar, d_arpar, w.u_choice, w.u_prop_ar, w.gauss_ar,
+                                      ar_prior[0], ar_prior[1], ar_prior[2], std::log(0.5), std::log(2.0),
+                                      g.vels.as<double>(), g.depths.as<double>(), g.nl.as<int>(),
+                                      g.idxar.as<int>(), g.arparb.as<double>(), g.mh_lpr.as<double>(),
+                                      g.mh_out.as<int>(), sc));
+            BatchArgs a = move_eval_args(B, ldk, d_src_offset, d_src_depth, d_tobs, NSrc, d_sigma, slot(2 + n_moves));
+            a.idxar = g.idxar.as<int>();
+            a.arpar = g.arparb.as<double>();
+            a.armx  = ar_prior[3];
+            if (e == cudaSuccess) ok(launch_move_eval(a, cfg, sc));
+            if (e == cudaSuccess)
+                ok(rtb::launch_ar_accept(d_idxar, d_arpar, g.idxar.as<int>(), g.arparb.as<double>(),
+                                         g.mh_lpr.as<double>(), d_logL, g.mh_ll.as<double>(), g.mh_out.as<int>(),
+                                         w.u_acc_ar, d_beta, B, w.acc_ar, sc));
+        }
         if (e == cudaSuccess) ok(rtb::launch_mcmc_finish(d_counter, d_k, d_pos, B, n_moves, w, d_tally, sc));
         cudaGraph_t graph = nullptr;
         cudaError_t e2 = cudaStreamEndCapture(sc, &graph);
@@ -1444,7 +1482,7 @@ int rtb200_mcmc_iterations_device(int *d_k, double *d_voro, double *d_logL, doub
         g.mc_key = key;
     }
     for (int it = 0; it < n_iterations; ++it) CK(cudaGraphLaunch(g.mc_exec, st));
-    g.launches += (long long)n_iterations * (3LL * n_moves + (kmin != kmax ? 3 : 0) + 3 + 2 + (n_moves > 0 ? 1 : 0));
+    g.launches += (long long)n_iterations * (3LL * n_moves + (kmin != kmax ? 3 : 0) + 3 + (d_idxar ? 3 : 0) + 2 + (n_moves > 0 ? 1 : 0));
     g.last = cfg;
     if (int rc = scratch_release(st, stream == nullptr)) return rc;
     if (!stream) CK(cudaStreamSynchronize(st));

@@ -86,22 +86,25 @@ struct BdPrior {
 // Workspace of one MCMC iteration run as a CUDA graph (rtb200_mcmc_iterations_device): every
 // deviate of the iteration, written by the library's Philox kernels and read by the move kernels,
 // and every move's outcome.  One caller-owned allocation, laid out as
-//   doubles: u_k | u_z | u_v | u_acc_bd | u_gate | gauss | u_acc_sd        [B] each
+//   doubles: u_k | u_z | u_v | u_acc_bd | u_gate | gauss | u_acc_sd |
+//            u_choice | u_prop_ar | gauss_ar | u_acc_ar                    [B] each
 //            dev [M][B] | u_acc [M][B]
-//   ints:    idel | acc_bd | acc_sd [B] each,  ivo | iwhich | acc_mh [M][B] each
+//   ints:    idel | acc_bd | acc_sd | acc_ar [B] each,  ivo | iwhich | acc_mh [M][B] each
 struct McmcWs {
-    double *u_k, *u_z, *u_v, *u_acc_bd, *u_gate, *gauss, *u_acc_sd, *dev, *u_acc;
-    int    *idel, *acc_bd, *acc_sd, *ivo, *iwhich, *acc_mh;
+    double *u_k, *u_z, *u_v, *u_acc_bd, *u_gate, *gauss, *u_acc_sd, *u_choice, *u_prop_ar, *gauss_ar,
+           *u_acc_ar, *dev, *u_acc;
+    int    *idel, *acc_bd, *acc_sd, *acc_ar, *ivo, *iwhich, *acc_mh;
 };
-inline size_t mcmc_ws_bytes(size_t B, size_t M) { return (7 + 2 * M) * B * 8 + (3 + 3 * M) * B * 4; }
+inline size_t mcmc_ws_bytes(size_t B, size_t M) { return (11 + 2 * M) * B * 8 + (4 + 3 * M) * B * 4; }
 inline McmcWs mcmc_ws_layout(void *base, size_t B, size_t M) {
     McmcWs w;
     double *d = static_cast<double *>(base);
     w.u_k = d; w.u_z = d + B; w.u_v = d + 2 * B; w.u_acc_bd = d + 3 * B; w.u_gate = d + 4 * B;
-    w.gauss = d + 5 * B; w.u_acc_sd = d + 6 * B; w.dev = d + 7 * B; w.u_acc = d + (7 + M) * B;
-    int *i = reinterpret_cast<int *>(d + (7 + 2 * M) * B);
-    w.idel = i; w.acc_bd = i + B; w.acc_sd = i + 2 * B; w.ivo = i + 3 * B; w.iwhich = i + (3 + M) * B;
-    w.acc_mh = i + (3 + 2 * M) * B;
+    w.gauss = d + 5 * B; w.u_acc_sd = d + 6 * B; w.u_choice = d + 7 * B; w.u_prop_ar = d + 8 * B;
+    w.gauss_ar = d + 9 * B; w.u_acc_ar = d + 10 * B; w.dev = d + 11 * B; w.u_acc = d + (11 + M) * B;
+    int *i = reinterpret_cast<int *>(d + (11 + 2 * M) * B);
+    w.idel = i; w.acc_bd = i + B; w.acc_sd = i + 2 * B; w.acc_ar = i + 3 * B; w.ivo = i + 4 * B;
+    w.iwhich = i + (4 + M) * B; w.acc_mh = i + (4 + 2 * M) * B;
     return w;
 }
 cudaError_t launch_mcmc_draw(const unsigned long long *counter, unsigned long long seed, const int *k,

@@ -296,11 +296,12 @@ def test_mcmc_workspace_layout():
     from raytracerfortran_b200 import _lib
     for B, M in ((1, 0), (7, 3), (100, 19)):
         n = _lib.load().rtb200_mcmc_workspace_bytes(B, M)
-        assert n == (7 + 2 * M) * B * 8 + (3 + 3 * M) * B * 4
+        assert n == (11 + 2 * M) * B * 8 + (4 + 3 * M) * B * 4
         ws = torch.zeros(n, dtype=torch.uint8)
         v = chains.mcmc_workspace_views(ws, B, M)
-        order = ["u_k", "u_z", "u_v", "u_acc_bd", "u_gate", "gauss", "u_acc_sd", "dev", "u_acc",
-                 "idel", "acc_bd", "acc_sd", "ivo", "iwhich", "acc_mh"]
+        order = ["u_k", "u_z", "u_v", "u_acc_bd", "u_gate", "gauss", "u_acc_sd", "u_choice", "u_prop_ar",
+                 "gauss_ar", "u_acc_ar", "dev", "u_acc", "idel", "acc_bd", "acc_sd", "acc_ar", "ivo", "iwhich",
+                 "acc_mh"]
         off = 0
         for name in order:
             t = v[name]

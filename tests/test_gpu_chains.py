@@ -648,3 +648,64 @@ def test_prior_sampling_mode_matches_oracle():
     finally:
         rt.set_option("ismpprior", 0)
         oracle.set_ismpprior(0)
+
+
+def test_mcmc_graph_with_the_ar_move_matches_oracle():
+    """IAR = 1 through the iteration graph: every likelihood uses the chains' AR(1) state and the
+    iteration ends with EXPLORE_MH's AR move (:583-631); the oracle replays the device-drawn
+    deviates: same outcomes, same idxarRT / arparRT / sigma / node bits."""
+    import torch
+    B, ldk, nsrc, M = 1200, 8, 20, 4
+    k, voro, so, sd, tobs, sigma, _ = _setup(B, ldk, nsrc, 111)
+    rng = np.random.default_rng(112)
+    prior, sp, pk = chains.prior_array(), chains.sd_prior_array(), chains.poisson_pk(3.01, 1, ldk)
+    prior[:2] /= 10.0
+    ap = chains.ar_prior_array()
+    ap[3] = 5.0
+    beta = 1.0 / 1.4 ** rng.integers(0, 4, B)
+    idxar = rng.integers(0, 2, B).astype(np.int32)
+    arpar = np.where(idxar == 1, rng.uniform(-0.5, 0.9, B), -1.5)
+    ll = np.empty(B)
+    for b in range(B):
+        pred = oracle.loglhood_rt(voro[b, 1, :k[b]], voro[b, 0, 1:k[b]], so, sd, tobs, sigma[b])[1]
+        ll[b] = oracle.loglhood_from_times_ar(pred, tobs, sigma[b], int(idxar[b]), float(arpar[b]), 5.0)
+    tk, tv, tl, tg, ti, ta, tb, ts, td, to = _dev(k, voro, ll, sigma, idxar, arpar, beta, so, sd, tobs)
+    g = chains.McmcGraph(tk, tv, tl, tg, tb, M, prior, sp, pk, 1, ldk, ts, td, to, seed=21, ar=(ti, ta, ap))
+    ck, cv, cl, cs, ci, ca = k.copy(), voro, ll, sigma.copy(), idxar, arpar
+    pos = np.zeros(B, dtype=np.int64)
+    seen = {1: 0, 0: 0, -1: 0}
+    try:
+        for it in range(3):
+            g.run(1)
+            torch.cuda.synchronize()
+            w = {n: t.cpu().numpy().copy() for n, t in g.views.items()}
+            oracle.set_chain_ar(ci, ca, 5.0)
+            r = oracle.bd_step_batch(ck, cv, cl, w["u_k"], w["idel"], w["u_z"], w["u_v"], w["u_acc_bd"], beta, cs,
+                                     prior, pk, 1, ldk, so, sd, tobs)
+            assert np.array_equal(w["acc_bd"], r["accept"]), f"bd {it}"
+            ck, cv, cl = r["k"], r["voro"], r["logL"]
+            period = np.maximum(2 * ck.astype(np.int64) - 1, 1)
+            for m in range(M):
+                r = oracle.mh_step_batch(ck, cv, cl, w["ivo"][m], w["iwhich"][m], w["dev"][m], w["u_acc"][m], beta, cs,
+                                         prior, so, sd, tobs)
+                assert np.array_equal(w["acc_mh"][m], r["accept"]), f"move {m}, iteration {it}"
+                cv, cl = r["voro"], r["logL"]
+            pos = (pos + M) % period
+            r = oracle.sd_step_batch(ck, cv, cl, cs, w["u_gate"], w["gauss"], w["u_acc_sd"], beta, sp, so, sd, tobs)
+            assert np.array_equal(w["acc_sd"], r["accept"]), f"sd {it}"
+            cl, cs = r["logL"], r["sigma"]
+            r = oracle.ar_step_batch(ck, cv, cl, cs, ci, ca, w["u_choice"], w["u_prop_ar"], w["gauss_ar"], w["u_acc_ar"],
+                                     beta, ap, so, sd, tobs)
+            assert np.array_equal(w["acc_ar"], r["accept"]), f"ar {it}"
+            cl, ci, ca = r["logL"], r["idxar"], r["arpar"]
+            for c_ in seen:
+                seen[c_] += int((w["acc_ar"] == c_).sum())
+            assert np.array_equal(tk.cpu().numpy(), ck)
+            assert np.array_equal(tv.cpu().numpy().view(np.uint64), cv.view(np.uint64)), f"iteration {it}"
+            assert np.array_equal(tg.cpu().numpy().view(np.uint64), cs.view(np.uint64))
+            assert np.array_equal(ti.cpu().numpy(), ci)
+            assert np.array_equal(ta.cpu().numpy().view(np.uint64), ca.view(np.uint64))
+    finally:
+        oracle.set_chain_ar()
+    assert all(n > 20 for n in seen.values()), seen
+    assert int(g.tally[4].sum().item()) == seen[1]
