@@ -48,7 +48,7 @@ while time.time() - t0 < args.seconds:
             so, sd = workloads.make_sources(S, int(rng.integers(1, 2**31)), near_critical=bool(L & 1))
             ref = oracle.dff_batch(v, z, nl, so, sd, want_p=True)
             got = rt.dff_batch(v, z, nl, so, sd, want_p=True)
-            assert rt.get_stat("variant") == 5
+            assert rt.get_stat("variant") == 9
             bad += int((got["timeP"].view(np.uint64) != ref["timeP"].view(np.uint64)).sum()) \
                 + int((got["p"].view(np.uint64) != ref["p"].view(np.uint64)).sum())
             n += S

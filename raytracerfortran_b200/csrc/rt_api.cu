@@ -219,7 +219,7 @@ int choose_cfg(int B, int ldv, int ldz, int nsrc, bool aligned, TileCfg &c) {
     // variant: 0 plain loops; 1 lane state machine; 3 the same with branch-free, two-step-unrolled
     // layer loops for deep models (more registers, 2 CTAs/SM); default: by depth
     c.variant = g.opt_variant < 0 ? (ldv >= kDeepLdv ? 3 : kShallowVariant)
-                                  : (g.opt_variant == 3 || g.opt_variant == 4 ? g.opt_variant : (g.opt_variant ? 1 : 0));
+                                  : (g.opt_variant >= 3 && g.opt_variant <= 5 ? g.opt_variant : (g.opt_variant ? 1 : 0));
     if (c.variant == 4 && ldv > 62) c.variant = 1;      // variant 4 keeps the layer count in 6 bits
     c.threads = g.opt_threads > 0 ? std::min(256, (g.opt_threads + 31) / 32 * 32) : 256;
     c.LP = std::max(ldv, 2) | 1;
@@ -263,6 +263,16 @@ int choose_cfg(int B, int ldv, int ldz, int nsrc, bool aligned, TileCfg &c) {
         }
     }
     const int ntiles = (B + c.M - 1) / c.M;
+    // Large batches of shallow models: variant 5 (one segment of the sorted ray list per warp, so
+    // a warp's lanes hold rays of one depth: -4.6 % on config 2).  Its tiles take a little longer
+    // from first to last warp (no rebalancing inside a tile), which only pays when every CTA slot
+    // works through many tiles: 60 000 models (3 rounds) and the 8192 x 256 shape (2 rounds) are
+    // 3-7 % slower with it, 150 000 models (8 rounds) 5 % faster.
+    if (g.opt_variant < 0 && c.variant == 1 && ntiles >= 6 * g.sms * occ) {
+        c.variant = 5;
+        const int occ5 = rtb::max_ctas_per_sm(c);
+        if (occ5 >= occ) occ = occ5; else c.variant = 1;
+    }
     c.grid = std::max(1, std::min(ntiles, g.sms * occ));
     g.last_ctas = occ;
     return 0;
@@ -477,7 +487,7 @@ int run_host_latency(const HostCall &h) {
     if (h.timeP) memcpy(h.timeP, out, (size_t)S * 8);
     if (h.p_out) memcpy(h.p_out, out + S, (size_t)S * 8);
     g.last = TileCfg{};
-    g.last.variant = 5;            // reported by rtb200_get_stat("variant")
+    g.last.variant = 9;            // what rtb200_get_stat("variant") reports for the latency kernel
     g.last.threads = std::min(S, 32) * 32;
     g.last.grid = (S + 31) / 32;
     return 0;

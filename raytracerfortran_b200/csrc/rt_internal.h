@@ -61,7 +61,7 @@ struct TileCfg {
     int threads;  // CTA size
     int grid;     // persistent CTAs
     int variant;  // 0: plain per-thread loops, 1: lane state machine with refill, 3: the same for deep models,
-                  // 4: level-synchronous ray queues (opt-in)
+                  // 4: level-synchronous ray queues (opt-in), 5: variant 1 with one list segment per warp
     int use_tma;  // rows are 16-byte aligned: stage with cp.async.bulk
     int logl_shuffle;  // reduce the residuals with warp shuffles (tree order) instead of source order
     size_t smem;  // dynamic shared memory bytes

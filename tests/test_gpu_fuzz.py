@@ -17,7 +17,7 @@ def same(got, want):
     return np.array_equal(np.isnan(g), nan) and np.array_equal(g[~nan].view(np.uint64), w[~nan].view(np.uint64))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4, 5])
 def test_hostile_models(variant):
     rt.set_option("variant", variant)
     rng = np.random.default_rng(2025)
