@@ -263,12 +263,16 @@ int choose_cfg(int B, int ldv, int ldz, int nsrc, bool aligned, TileCfg &c) {
         }
     }
     const int ntiles = (B + c.M - 1) / c.M;
-    // Large batches of shallow models: variant 5 (one segment of the sorted ray list per warp, so
-    // a warp's lanes hold rays of one depth: -4.6 % on config 2).  Its tiles take a little longer
-    // from first to last warp (no rebalancing inside a tile), which only pays when every CTA slot
-    // works through many tiles: 60 000 models (3 rounds) and the 8192 x 256 shape (2 rounds) are
-    // 3-7 % slower with it, 150 000 models (8 rounds) 5 % faster.
-    if (g.opt_variant < 0 && c.variant == 1 && ntiles >= 6 * g.sms * occ) {
+    // Shallow models: variant 5 (one segment of the sorted ray list per warp, so a warp's lanes
+    // hold rays of one depth: -4.6 % on config 2) where its tiles' longer first-to-last-warp time
+    // (nothing rebalances the warps inside a tile) is not exposed at the end of the launch: when
+    // every CTA slot works through many tiles (150 000 models x 64 sources, 8 rounds: 5 % faster),
+    // and when the launch is a single wave of full tiles anyway (4096 states x 256 sources: 2-3 %
+    // faster).  In between it loses: 60 000 models (3 rounds) and the 8192 x 256 shape (2 rounds)
+    // are 3-7 % slower with it, so those keep variant 1.
+    const int slots = g.sms * occ;
+    if (g.opt_variant < 0 && c.variant == 1 &&
+        (ntiles >= 6 * slots || (ntiles <= slots && c.M * c.SC >= 1024))) {
         c.variant = 5;
         const int occ5 = rtb::max_ctas_per_sm(c);
         if (occ5 >= occ) occ = occ5; else c.variant = 1;
