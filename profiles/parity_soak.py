@@ -21,9 +21,10 @@ rays = mism = batches = 0
 kinds = {}
 while time.time() - t0 < args.seconds:
     kind = ["shallow", "deep-critical", "ragged", "kmode", "one-model"][batches % 5]
-    # round 2: every third batch through the opt-in queue kernel (variant 4; deep models fall back
-    # to their own kernel), and a kind of its own for the one-model latency kernel
-    rt.set_option("variant", 4 if batches % 3 == 2 else -1)
+    # round 2: the batches rotate over the default choice (variant 1, 3 or 5 by shape), variant 5
+    # (one list segment per warp), the opt-in queue kernel (variant 4; deep models fall back to
+    # their own kernel) and variant 1; a kind of its own for the one-model latency kernel
+    rt.set_option("variant", [-1, 5, 4, 1][batches % 4])
     seed = int(rng.integers(1, 2**31))
     if kind == "shallow":
         L, S, B = int(rng.integers(1, 13)), int(rng.integers(8, 129)), 60000
@@ -70,14 +71,15 @@ while time.time() - t0 < args.seconds:
         ref = oracle.dff_batch(vv, zz, nlr, so, sd)
         bad = int((pred.view(np.uint64) != ref["timeP"].view(np.uint64)).sum())
         rays += B * S; mism += bad; batches += 1
-        kinds[kind] = kinds.get(kind, 0) + B * S
+        tag = kind + " (variant %d)" % int(rt.get_stat("variant"))
+        kinds[tag] = kinds.get(tag, 0) + B * S
         continue
     ref = oracle.dff_batch(v, z, nl, so, sd, want_p=True)
     got = rt.dff_batch(v, z, nl, so, sd, want_p=True)
     bad = int((got["timeP"].view(np.uint64) != ref["timeP"].view(np.uint64)).sum()) \
         + int((got["p"].view(np.uint64) != ref["p"].view(np.uint64)).sum())
     rays += B * S; mism += bad; batches += 1
-    tag = kind + (" (variant 4)" if rt.get_stat("variant") == 4 else "")
+    tag = kind + " (variant %d)" % int(rt.get_stat("variant"))
     kinds[tag] = kinds.get(tag, 0) + B * S
 print(json.dumps({"seconds": time.time() - t0, "batches": batches, "rays_compared": rays,
                   "bit_mismatches": mism, "rays_by_kind": kinds, "seed": args.seed}))
