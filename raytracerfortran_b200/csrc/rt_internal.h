@@ -66,6 +66,10 @@ struct TileCfg {
     int logl_shuffle;  // reduce the residuals with warp shuffles (tree order) instead of source order
     size_t smem;  // dynamic shared memory bytes
     QGeom  q;     // filled in by launch_batch
+    double kc[6]; // the solver's constants (filled in by launch_batch).  Read only when the kernels are
+                  // built with -DRTB_CONST_BANK (constants as kernel parameters instead of immediates
+                  // built in registers on every pass: six LDC against ten moves, measured 0.8 % slower,
+                  // profiles/r02_phase_ab.txt), so the shipped kernels do not touch it
 };
 
 // Prior and proposal scales of the fixed-dimension MH move (read_input.f90:207-214).
