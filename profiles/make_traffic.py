@@ -31,7 +31,9 @@ d = {"source": "profiles/r02_c2_ncu_full.txt (ncu --set full --clock-control non
      "fp64_pipe_active_pct": round(get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", False), 2),
      "issue_active_pct": round(get("smsp__issue_active.avg.pct_of_peak_sustained_active", False), 2),
      "warp_instructions": int(get("smsp__inst_executed.sum", False)),
-     "lane_efficiency": get("smsp__thread_inst_executed_per_inst_executed.ratio", False) / 32.0,
+     "threads_per_warp_instruction": get("smsp__thread_inst_executed_per_inst_executed.ratio", False),
+     "threads_per_warp_instruction_note": "ncu's thread_inst/inst; idle lanes execute the convergent state update on dead "
+                                          "values, so this is not the share of useful lanes (profiles/lane_hist.py measures that)",
      "kernel_sources_sha": kernel_sources_sha(), "commit": commit, "date": datetime.date.today().isoformat()}
 for o in outs:
     json.dump(d, open(o, "w"), indent=1)
