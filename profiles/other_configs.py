@@ -57,7 +57,7 @@ def main():
         kmode=False, v=v, z=z, n=nl, src=workloads.make_sources(c5["nsrc"], c5["seed"], near_critical=True))
 
     for name, s in shapes.items():
-        if "config5" in name and args.opt:
+        if "config5" in name and args.opt and not args.only:
             continue
         if args.only and args.only not in name:
             continue
