@@ -185,3 +185,39 @@ def test_next_row_n3_replica_sweep_over_a_sample_file(tmp_path):
                                                   tobs, smp["sdparRT"][j, 0])
         assert np.array_equal(bits(pred[j]), bits(w_pred))
         assert logl_close(np.array([ll[j]]), np.array([w_ll]), nsrc, smp["sdparRT"][j])
+
+
+def test_default_kernel_choice_by_shape():
+    """Which kernel the library picks on its own (rt_api.cu choose_cfg): the deep-model kernel from
+    40 velocities per row; for shallow models the segment kernel (5) when the batch is a long queue
+    of tiles or a single wave of full tiles, the shared-pointer kernel (1) in between; the one-model
+    kernel (reported as 9) for a single model.  The results are bit-identical whichever runs (the
+    parity tests force each one); this pins the rule itself."""
+    import torch
+    from raytracerfortran_b200 import device
+    dev = torch.device("cuda:0")
+    f = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    sms = int(rt.get_stat("sms")) or 148
+
+    def variant_for(B, L, S, kmode=False, seed=3):
+        if kmode:
+            n, v, z = workloads.make_transd_models(B, L, seed)
+        else:
+            v, z, n = workloads.make_models(B, L, seed)
+        so, sd = workloads.make_sources(S, seed)
+        out = device.dff_batch_device(f(v), f(z), f(n.astype(np.int32)), f(so), f(sd), want_times=True,
+                                      kmode=kmode)
+        torch.cuda.synchronize()
+        slots = sms * int(rt.get_stat("ctas_per_sm"))
+        tiles = -(-B // int(rt.get_stat("tile_models")))
+        return int(rt.get_stat("variant")), tiles, slots
+
+    rt.set_option("variant", -1)
+    v, tiles, slots = variant_for(8 * sms * 4 * 32, 10, 64)          # a long queue of tiles
+    assert tiles >= 6 * slots and v == 5
+    v, tiles, slots = variant_for(3 * sms * 4 * 32, 10, 64)          # three rounds
+    assert slots < tiles < 6 * slots and v == 1
+    v, tiles, slots = variant_for(4096, 30, 256, kmode=True)         # one wave of full tiles (config 3)
+    assert tiles <= slots and v == 5
+    v, _, _ = variant_for(2048, 50, 128)                             # deep models
+    assert v == 3
