@@ -14,8 +14,10 @@
  *                      raytracerR-export-data-to-MCMC.Rmd:61);
  *   - the caller owns every buffer; the library keeps no result state between calls
  *     (device buffers and streams are cached internally and reused);
- *   - one calling thread per process; one process per GPU (device = RTB200_DEVICE, else
- *     LOCAL_RANK, else 0, unless rtb200_init() chose one);
+ *   - one context and one GPU per process (device = RTB200_DEVICE, else LOCAL_RANK, else 0,
+ *     unless rtb200_init() chose one); every entry takes one process-wide lock, so calls from
+ *     several host threads are safe and run one after the other (rtb200_last_error() is the
+ *     last error of any thread);
  *   - there is NO CPU fallback: without a usable CUDA device the Fortran-style entries fill
  *     their outputs with NaN, print one line to stderr and record rtb200_last_error();
  *     the int-returning entries return a non-zero status.

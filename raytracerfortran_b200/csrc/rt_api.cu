@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -805,6 +806,13 @@ void dff_impl(const double *vels, const double *depths, int NL, const double *of
 
 }  // namespace
 
+// Every public entry takes this lock: calls from several host threads are serialised (the context
+// below them -- cached buffers, options, the scratch of the chain moves -- is one per process).
+static std::recursive_mutex g_api_mu;
+struct ApiLock {
+    std::lock_guard<std::recursive_mutex> l{g_api_mu};
+};
+
 extern "C" {
 
 #ifdef RTB200_DFF_IS_7ARG
@@ -818,6 +826,7 @@ extern "C" {
 void RTB200_DFF8(const double *vels, const double *depths, const int *NLayers,
                  const double *src_offset, const double *src_depth, const int *NSrc,
                  double *timeP, const int *keep_delta) {
+    ApiLock api_lock_;
     dff_impl(vels, depths, *NLayers, src_offset, src_depth, *NSrc, timeP,
              keep_delta ? *keep_delta : -1);
 }
@@ -825,12 +834,14 @@ void RTB200_DFF8(const double *vels, const double *depths, const int *NLayers,
 void RTB200_DFF7(const double *vels, const double *depths, const int *NLayers,
                  const double *src_offset, const double *src_depth, const int *NSrc,
                  double *timeP) {
+    ApiLock api_lock_;
     dff_impl(vels, depths, *NLayers, src_offset, src_depth, *NSrc, timeP, -1);
 }
 
 void tracerays_(const double *vels, const double *depths, const int *NLayers,
                 const double *src_offset, const double *src_depth, const int *NSrc,
                 double *timeP, const int *keep_delta) {
+    ApiLock api_lock_;
     dff_impl(vels, depths, *NLayers, src_offset, src_depth, *NSrc, timeP,
              keep_delta ? *keep_delta : -1);
 }
@@ -853,6 +864,7 @@ int dff_batch(const double *vels, const double *depths, const int *nlayers, cons
               const int *ldv, const int *ldz, const double *src_offset, const double *src_depth,
               const int *NSrc, double *timeP, const double *tobs, const double *sigma,
               double *logL, double *p_out) {
+    ApiLock api_lock_;
     HostCall h{};
     h.vels = vels; h.depths = depths; h.nlayers = nlayers;
     h.B = *B; h.ldv = *ldv; h.ldz = *ldz; h.kmode = 0;
@@ -866,6 +878,7 @@ void dff_batch_status(const double *vels, const double *depths, const int *nlaye
                       const double *src_depth, const int *NSrc, double *timeP, const double *tobs,
                       const double *sigma, double *logL, double *p_out, const int *want,
                       int *status) {
+    ApiLock api_lock_;
     const bool wt = want && want[0], wl = want && want[1], wp = want && want[2];
     const int rc = dff_batch(vels, depths, nlayers, B, ldv, ldz, src_offset, src_depth, NSrc,
                              wt ? timeP : nullptr, wl ? tobs : nullptr, wl ? sigma : nullptr,
@@ -879,6 +892,7 @@ void dff_batch_status_(const double *vels, const double *depths, const int *nlay
                        const double *src_depth, const int *NSrc, double *timeP, const double *tobs,
                        const double *sigma, double *logL, double *p_out, const int *want,
                        int *status) {
+    ApiLock api_lock_;
     dff_batch_status(vels, depths, nlayers, B, ldv, ldz, src_offset, src_depth, NSrc, timeP, tobs,
                      sigma, logL, p_out, want, status);
 }
@@ -887,6 +901,7 @@ int loglhood_batch(const int *k, const double *vp, const double *ziface, const i
                    const int *ldv, const int *ldz, const double *src_offset,
                    const double *src_depth, const int *NSrc, const double *tobs,
                    const double *sigma, double *logL, double *tpred) {
+    ApiLock api_lock_;
     HostCall h{};
     h.vels = vp; h.depths = ziface; h.nlayers = k;
     h.B = *B; h.ldv = *ldv; h.ldz = *ldz; h.kmode = 1;
@@ -900,6 +915,7 @@ int loglhood_batch_ar(const int *k, const double *vp, const double *ziface, cons
                       const double *src_depth, const int *NSrc, const double *tobs,
                       const double *sigma, const int *idxar, const double *arpar,
                       const double *armx, double *logL, double *tpred) {
+    ApiLock api_lock_;
     HostCall h{};
     h.vels = vp; h.depths = ziface; h.nlayers = k;
     h.B = *B; h.ldv = *ldv; h.ldz = *ldz; h.kmode = 1;
@@ -914,6 +930,7 @@ int loglhood_batch_voro(const int *k, const double *voro, const int *B, const in
                         const double *src_offset, const double *src_depth, const int *NSrc,
                         const double *tobs, const double *sigma, double *logL, double *tpred,
                         double *voro_sorted) {
+    ApiLock api_lock_;
     if (int rc = ensure_init()) return rc;
     g.err.clear();
     g.kernel_ms = g.total_ms = 0.0;
@@ -971,6 +988,7 @@ int rtb200_dff_batch_device(const double *d_vels, const double *d_depths, const 
                             const double *d_src_depth, int NSrc, double *d_timeP,
                             const double *d_tobs, const double *d_sigma, double *d_logL,
                             double *d_p_out, int kmode, void *stream) {
+    ApiLock api_lock_;
     if (int rc = ensure_init()) return rc;
     g.err.clear();
     if (B <= 0 || NSrc <= 0) return 0;
@@ -1061,6 +1079,7 @@ int rtb200_mh_step_device(const int *d_k, double *d_voro, double *d_logL, int B,
                           const double *prior, const double *d_src_offset,
                           const double *d_src_depth, const double *d_tobs, int NSrc,
                           int *d_accept, void *stream) {
+    ApiLock api_lock_;
     return rtb200_mh_step_device_ev(d_k, d_voro, d_logL, B, ldk, d_ivo, d_iwhich, d_cauchy, d_uacc,
                                     d_beta, d_sigma, prior, d_src_offset, d_src_depth, d_tobs, NSrc,
                                     d_accept, stream, nullptr, 0);
@@ -1072,6 +1091,7 @@ int rtb200_mh_step_device_ev(const int *d_k, double *d_voro, double *d_logL, int
                              const double *prior, const double *d_src_offset,
                              const double *d_src_depth, const double *d_tobs, int NSrc,
                              int *d_accept, void *stream, void *beta_ready_event, int enos) {
+    ApiLock api_lock_;
     if (int rc = ensure_init()) return rc;
     g.err.clear();
     if (B <= 0) return 0;
@@ -1118,6 +1138,7 @@ int rtb200_mh_moves_device(const int *d_k, double *d_voro, double *d_logL, int B
                            const double *d_sigma, const double *prior, const double *d_src_offset,
                            const double *d_src_depth, const double *d_tobs, int NSrc,
                            int *d_accept, void *stream) {
+    ApiLock api_lock_;
     return rtb200_mh_moves_device_ex(d_k, d_voro, d_logL, B, ldk, n_moves, d_ivo, d_iwhich, d_cauchy, d_uacc,
                                      d_beta, d_sigma, prior, d_src_offset, d_src_depth, d_tobs, NSrc,
                                      d_accept, stream, 0);
@@ -1129,6 +1150,7 @@ int rtb200_mh_moves_device_ex(const int *d_k, double *d_voro, double *d_logL, in
                               const double *d_sigma, const double *prior, const double *d_src_offset,
                               const double *d_src_depth, const double *d_tobs, int NSrc,
                               int *d_accept, void *stream, int enos) {
+    ApiLock api_lock_;
     if (int rc = ensure_init()) return rc;
     g.err.clear();
     if (B <= 0 || n_moves <= 0) return 0;
@@ -1204,6 +1226,7 @@ int rtb200_bd_step_device(int *d_k, double *d_voro, double *d_logL, int B, int l
                           const double *d_sigma, const double *prior, const double *pk, int kmin,
                           int kmax, const double *d_src_offset, const double *d_src_depth,
                           const double *d_tobs, int NSrc, int *d_accept, void *stream) {
+    ApiLock api_lock_;
     return rtb200_bd_step_device_ex(d_k, d_voro, d_logL, B, ldk, d_uk, d_idel, d_uz, d_uv, d_uacc, d_beta,
                                     d_sigma, prior, pk, kmin, kmax, d_src_offset, d_src_depth, d_tobs, NSrc,
                                     d_accept, stream, 0);
@@ -1215,6 +1238,7 @@ int rtb200_bd_step_device_ex(int *d_k, double *d_voro, double *d_logL, int B, in
                              const double *d_sigma, const double *prior, const double *pk, int kmin,
                              int kmax, const double *d_src_offset, const double *d_src_depth,
                              const double *d_tobs, int NSrc, int *d_accept, void *stream, int enos) {
+    ApiLock api_lock_;
     if (int rc = ensure_init()) return rc;
     g.err.clear();
     if (B <= 0) return 0;
@@ -1260,6 +1284,7 @@ int rtb200_sd_step_device(const int *d_k, const double *d_voro, double *d_logL, 
                           const double *d_uacc, const double *d_beta, const double *sd_prior,
                           const double *d_src_offset, const double *d_src_depth,
                           const double *d_tobs, int NSrc, int *d_accept, void *stream) {
+    ApiLock api_lock_;
     if (int rc = ensure_init()) return rc;
     g.err.clear();
     if (B <= 0) return 0;
@@ -1294,6 +1319,7 @@ int rtb200_sd_step_device(const int *d_k, const double *d_voro, double *d_logL, 
 }
 
 int rtb200_set_chain_ar(const int *d_idxar, const double *d_arpar, double armx) {
+    ApiLock api_lock_;
     g.err.clear();
     if ((d_idxar == nullptr) != (d_arpar == nullptr)) return fail("rtb200_set_chain_ar needs both arrays or neither");
     g.chain_idxar = d_idxar;
@@ -1308,6 +1334,7 @@ int rtb200_ar_step_device(const int *d_k, const double *d_voro, double *d_logL,
                           const double *d_uacc, const double *d_beta, const double *ar_prior,
                           const double *d_src_offset, const double *d_src_depth,
                           const double *d_tobs, int NSrc, int *d_accept, void *stream) {
+    ApiLock api_lock_;
     if (int rc = ensure_init()) return rc;
     g.err.clear();
     if (B <= 0) return 0;
@@ -1349,6 +1376,7 @@ int rtb200_ar_step_device(const int *d_k, const double *d_voro, double *d_logL,
 }
 
 size_t rtb200_mcmc_workspace_bytes(int B, int n_moves) {
+    ApiLock api_lock_;
     return (B > 0 && n_moves >= 0) ? rtb::mcmc_ws_bytes((size_t)B, (size_t)n_moves) : 0;
 }
 
@@ -1365,6 +1393,7 @@ int rtb200_mcmc_iterations_device(int *d_k, double *d_voro, double *d_logL, doub
                                   void *d_workspace, long long *d_tally, int n_iterations,
                                   int *d_idxar, double *d_arpar, const double *ar_prior,
                                   void *stream) {
+    ApiLock api_lock_;
     if (int rc = ensure_init()) return rc;
     g.err.clear();
     if (B <= 0 || n_iterations <= 0) return 0;
@@ -1505,6 +1534,7 @@ int rtb200_mcmc_iterations_device(int *d_k, double *d_voro, double *d_logL, doub
 
 int rtb200_swap_pack_device(const double *d_logL, const double *d_beta, int n, double *d_out,
                             void *stream) {
+    ApiLock api_lock_;
     if (int rc = ensure_init()) return rc;
     g.err.clear();
     if (n <= 0) return 0;
@@ -1519,6 +1549,7 @@ int rtb200_swap_pack_device(const double *d_logL, const double *d_beta, int n, d
 int rtb200_swap_round_device(const double *d_all, int n, int lo, int n_local,
                              unsigned long long seed, unsigned long long round,
                              double *d_beta_local, int *d_accept, int *d_partner, void *stream) {
+    ApiLock api_lock_;
     if (int rc = ensure_init()) return rc;
     g.err.clear();
     if (n <= 0 || n_local <= 0) return 0;
@@ -1533,12 +1564,14 @@ int rtb200_swap_round_device(const double *d_all, int n, int lo, int n_local,
 }
 
 int rtb200_init(int device) {
+    ApiLock api_lock_;
     const int rc = ensure_init(device);
     if (rc == 0) g.err.clear();
     return rc;
 }
 
 void rtb200_shutdown(void) {
+    ApiLock api_lock_;
     if (!g.inited || !g.ok) { g.inited = false; return; }
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
@@ -1585,12 +1618,14 @@ void rtb200_shutdown(void) {
 const char *rtb200_last_error(void) { return g.err.c_str(); }
 
 int rtb200_device_count(void) {
+    ApiLock api_lock_;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
 
 int rtb200_set_option(const char *name, double value) {
+    ApiLock api_lock_;
     const int v = (int)value;
     if (!strcmp(name, "variant")) g.opt_variant = v < 0 ? -1 : v;
     else if (!strcmp(name, "threads")) g.opt_threads = v;
@@ -1610,6 +1645,7 @@ int rtb200_set_option(const char *name, double value) {
 }
 
 double rtb200_get_stat(const char *name) {
+    ApiLock api_lock_;
     if (!strcmp(name, "kernel_ms")) return g.kernel_ms;
     if (!strcmp(name, "total_ms")) return g.total_ms;
     if (!strcmp(name, "launches")) return (double)g.launches;
@@ -1625,6 +1661,7 @@ double rtb200_get_stat(const char *name) {
 }
 
 double rtb200_fp64_peak_tflops(int repeats) {
+    ApiLock api_lock_;
     if (ensure_init()) return std::numeric_limits<double>::quiet_NaN();
     g.err.clear();
     double tf = 0.0;
@@ -1635,6 +1672,7 @@ double rtb200_fp64_peak_tflops(int repeats) {
 }
 
 double rtb200_selftest_fast_division(double samples, unsigned long long seed) {
+    ApiLock api_lock_;
     if (ensure_init()) return -1.0;
     g.err.clear();
     double bad = -1.0;

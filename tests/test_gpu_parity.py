@@ -447,3 +447,39 @@ def test_dff_batch_status_entry_for_r():
     lib.dff_batch_status(P(v), P(z), nl.ctypes.data_as(ip), ci(B), ci(0), ci(z.shape[1]), P(so), P(sd), ci(nsrc),
                          P(t), P(tobs), P(sigma), P(ll), P(p), want.ctypes.data_as(ip), C.byref(status))
     assert status.value != 0 and "ldv" in _lib.last_error()
+
+
+def test_concurrent_host_threads_are_serialised():
+    """The library keeps one context per process; every public entry takes one lock, so callers on
+    several host threads (ctypes drops the GIL during the call) get the answers they would get
+    alone: one-model dff_ calls, batched calls and option reads interleaved from four threads."""
+    import threading
+    rng = np.random.default_rng(77)
+    jobs = []
+    for t in range(4):
+        L, S, B = int(rng.integers(2, 12)), int(rng.integers(8, 80)), int(rng.integers(50, 400))
+        v, z, nl = workloads.make_models(B, L, 500 + t)
+        so, sd = workloads.make_sources(S, 600 + t)
+        jobs.append((v, z, nl, so, sd, oracle.dff_batch(v, z, nl, so, sd)["timeP"]))
+    errors = []
+
+    def worker(t):
+        v, z, nl, so, sd, want = jobs[t]
+        try:
+            for it in range(25):
+                got = rt.dff_batch(v, z, nl, so, sd)["timeP"]
+                if not np.array_equal(got.view(np.uint64), want.view(np.uint64)):
+                    errors.append((t, it, "batch"))
+                one = rt.dff(v[0, :nl[0] + 1], z[0, :nl[0]], so, sd)
+                if not np.array_equal(np.asarray(one).view(np.uint64), want[0].view(np.uint64)):
+                    errors.append((t, it, "one model"))
+                rt.get_stat("variant")
+        except Exception as e:                      # noqa: BLE001 - reported below
+            errors.append((t, -1, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[:5]
