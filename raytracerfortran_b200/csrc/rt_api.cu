@@ -1615,7 +1615,13 @@ void rtb200_shutdown(void) {
     g.inited = g.ok = false;
 }
 
-const char *rtb200_last_error(void) { return g.err.c_str(); }
+const char *rtb200_last_error(void) {
+    // a copy per calling thread: the pointer stays valid while other threads go on calling
+    ApiLock api_lock_;
+    static thread_local std::string copy;
+    copy = g.err;
+    return copy.c_str();
+}
 
 int rtb200_device_count(void) {
     ApiLock api_lock_;
